@@ -1,0 +1,176 @@
+"""Pins the CPU oracle (oracle/) against outputs of the reference itself.
+
+tests/golden/*.npz were produced by oracle/make_golden.py running the unmodified
+reference (main.load_preprocessed_data, models.*, main.bpr_loss_reg, torch Adam,
+main.evaluate) on CPU.  Integer / index work must be bit-exact; fp32 propagation is
+bit-exact too (sequential FMA); loss / grads / Adam within 1e-5 relative.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from oracle import lgcn_oracle as orc
+
+CASES = ["tiny_lightgcn_d64_k3", "tiny_lightgcn_d128_k4", "tiny_lightgcn_brand_d64_k3",
+         "tiny_fusion_d64_k3"]
+TOL = 1e-5
+
+
+def _adj(g):
+    ib = (g["item_brand_item"], g["item_brand_brand"]) if "item_brand_item" in g else None
+    return orc.build_norm_adj(g["train_user"], g["train_item"], int(g["num_users"]),
+                              int(g["num_items"]), int(g["num_brands"]), ib)
+
+
+def _tables(g, prefix):
+    item_key = "item_id_embedding.weight" if prefix + "/item_id_embedding.weight" in g \
+        else "item_embedding.weight"
+    return (g[prefix + "/user_embedding.weight"], g[prefix + "/" + item_key],
+            g[prefix + "/brand_embedding.weight"], item_key)
+
+
+def _e0(g, prefix):
+    u, i, b, key = _tables(g, prefix)
+    if key == "item_id_embedding.weight":
+        i_in, pre = orc.fusion_forward(i, g["init/item_content_embedding"],
+                                       g[prefix + "/item_fusion_layer.weight"],
+                                       g[prefix + "/item_fusion_layer.bias"])
+    else:
+        i_in, pre = i, None
+    return np.concatenate([u, i_in, b], 0), pre
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_validation_split_first_row_per_user(golden, case):
+    g = golden(case)
+    from gcn_recommendation_b200.synth import Interactions
+    inter = Interactions(int(g["num_users"]), int(g["num_items"]), int(g["num_brands"]),
+                         g["all_train_user"], g["all_train_item"], g["test_user"], g["test_item"])
+    tu, ti, vu, vi = inter.split_validation()
+    assert np.array_equal(tu, g["train_user"]) and np.array_equal(ti, g["train_item"])
+    assert np.array_equal(vu, g["val_user"]) and np.array_equal(vi, g["val_item"])
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_adjacency_bit_exact(golden, case):
+    g = golden(case)
+    a = _adj(g)
+    N = int(g["num_users"]) + int(g["num_items"]) + int(g["num_brands"])
+    rows = np.repeat(np.arange(N), np.diff(a["rowptr"])).astype(np.int32)
+    assert np.array_equal(rows, g["adj_row"])
+    assert np.array_equal(a["col"], g["adj_col"])
+    assert np.array_equal(a["val"].view(np.uint32), g["adj_val"].view(np.uint32))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_forward_bit_exact_vs_torch_sparse(golden, case):
+    g = golden(case)
+    a = _adj(g)
+    E0, _ = _e0(g, "init")
+    F, _ = orc.propagate(a["rowptr"], a["col"], a["val"], E0, int(g["K"]))
+    U, I = int(g["num_users"]), int(g["num_items"])
+    ref = np.concatenate([g["fwd/user"], g["fwd/item"], g["fwd/brand"]], 0)
+    if "fusion" in case:     # sgemm order is not pinned -> 1e-5
+        mx, fro = rel_err(F, ref)
+        assert mx < TOL and fro < TOL
+    else:
+        assert np.array_equal(F.view(np.uint32), ref.view(np.uint32))
+    assert F[:U].shape == g["fwd/user"].shape and F[U:U + I].shape == g["fwd/item"].shape
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_loss_grads_adam(golden, case):
+    g = golden(case)
+    a = _adj(g)
+    U, I, K = int(g["num_users"]), int(g["num_items"]), int(g["K"])
+    E0, pre = _e0(g, "init")
+    F, _ = orc.propagate(a["rowptr"], a["col"], a["val"], E0, K)
+    u0, i0, b0, item_key = _tables(g, "init")
+    loss, gF, gU, gI = orc.bpr_loss(F, u0, i0, g["batch_users"][0], g["batch_pos"][0],
+                                    g["batch_neg"][0], U, float(g["lam"]))
+    assert abs(loss - g["losses"][0]) <= TOL * abs(g["losses"][0])
+    dE0 = orc.propagate_backward(a["rowptr"], a["col"], a["val"], gF, K)
+    grads = {"user_embedding.weight": dE0[:U] + gU, "brand_embedding.weight": dE0[U + I:]}
+    if pre is None:
+        grads[item_key] = dE0[U:U + I] + gI
+    else:
+        gE, gW, gb = orc.fusion_backward(i0, g["init/item_content_embedding"],
+                                         g["init/item_fusion_layer.weight"], pre, dE0[U:U + I])
+        grads[item_key] = gE + gI
+        grads["item_fusion_layer.weight"] = gW
+        grads["item_fusion_layer.bias"] = gb
+    for k, v in grads.items():
+        mx, fro = rel_err(v, g["grad1/" + k])
+        assert mx < TOL and fro < TOL, (k, mx, fro)
+    for k, gr in grads.items():
+        p = g["init/" + k].copy()
+        m = np.zeros_like(p)
+        v = np.zeros_like(p)
+        orc.adam_step(p, g["grad1/" + k], m, v, 1, lr=float(g["lr"]))
+        mx, fro = rel_err(p, g["step1/" + k])
+        assert mx < TOL and fro < TOL, (k, mx, fro)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_multi_step_training_tracks_reference(golden, case):
+    """Oracle train loop (propagate -> bpr -> backward -> adam) vs the reference's losses."""
+    g = golden(case)
+    a = _adj(g)
+    U, I, K = int(g["num_users"]), int(g["num_items"]), int(g["K"])
+    names = [k[5:] for k in g if k.startswith("init/") and k != "init/item_content_embedding"]
+    P = {k: g["init/" + k].copy() for k in names}
+    M = {k: np.zeros_like(P[k]) for k in names}
+    V = {k: np.zeros_like(P[k]) for k in names}
+    fusion = "item_fusion_layer.weight" in P
+    ik = "item_id_embedding.weight" if fusion else "item_embedding.weight"
+    for s in range(len(g["losses"])):
+        if fusion:
+            it, pre = orc.fusion_forward(P[ik], g["init/item_content_embedding"],
+                                         P["item_fusion_layer.weight"], P["item_fusion_layer.bias"])
+        else:
+            it, pre = P[ik], None
+        E0 = np.concatenate([P["user_embedding.weight"], it, P["brand_embedding.weight"]], 0)
+        F, _ = orc.propagate(a["rowptr"], a["col"], a["val"], E0, K)
+        loss, gF, gU, gI = orc.bpr_loss(F, P["user_embedding.weight"], P[ik], g["batch_users"][s],
+                                        g["batch_pos"][s], g["batch_neg"][s], U, float(g["lam"]))
+        assert abs(loss - g["losses"][s]) <= 2e-5 * abs(g["losses"][s]), (s, loss, g["losses"][s])
+        dE0 = orc.propagate_backward(a["rowptr"], a["col"], a["val"], gF, K)
+        G = {"user_embedding.weight": dE0[:U] + gU, "brand_embedding.weight": dE0[U + I:]}
+        if fusion:
+            gE, gW, gb = orc.fusion_backward(P[ik], g["init/item_content_embedding"],
+                                             P["item_fusion_layer.weight"], pre, dE0[U:U + I])
+            G[ik] = gE + gI
+            G["item_fusion_layer.weight"], G["item_fusion_layer.bias"] = gW, gb
+        else:
+            G[ik] = dE0[U:U + I] + gI
+        for k in names:
+            orc.adam_step(P[k], G[k], M[k], V[k], s + 1, lr=float(g["lr"]))
+    for k in names:
+        # Adam divides by sqrt(v): elements whose gradient is ~0 amplify fp32 rounding
+        # differences (m/sqrt(v) ~ sign(g)), so the element-wise max is looser than the norm.
+        mx, fro = rel_err(P[k], g["final/" + k])
+        assert mx < 1e-3 and fro < 1e-5, (k, mx, fro)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_eval_topk_and_metrics(golden, case):
+    g = golden(case)
+    users, targets = orc.eval_pairs(g["val_user"], g["val_item"])
+    assert np.array_equal(users, g["eval/users"])
+    mr, mc = orc.mask_csr(users, g["train_user"], g["train_item"], int(g["num_users"]))
+    ids, sc = orc.score_topk(g["eval/F_user"], g["eval/F_item"], users, mr, mc, 20)
+    ref_ids, ref_sc = g["eval/topk_ids"], g["eval/topk_scores"]
+    # ids must agree wherever the reference's neighbouring scores are not fp32 near-ties
+    same = ids == ref_ids
+    if not same.all():
+        bad_rows = np.where(~same.all(1))[0]
+        for r in bad_rows:
+            assert sorted(ids[r].tolist()) == sorted(ref_ids[r].tolist()) or \
+                np.abs(np.sort(sc[r]) - np.sort(ref_sc[r])).max() <= 1e-6 * np.abs(ref_sc[r]).max()
+            gap = np.abs(np.diff(ref_sc[r]))
+            assert gap.min() <= 4e-7 * np.abs(ref_sc[r]).max(), "id mismatch without a near-tie"
+    mx, _ = rel_err(sc, ref_sc)
+    assert mx < TOL
+    rec, ndcg = orc.recall_ndcg(ids, targets)
+    assert rec == pytest.approx(float(g["eval/recall"]), abs=1e-12)
+    assert ndcg == pytest.approx(float(g["eval/ndcg"]), abs=1e-12)
