@@ -1,0 +1,253 @@
+"""Native LightGCN trainer / evaluator: the throughput vehicle (mode 2).
+
+One training step is what reference ``main.py:488-531`` does per batch -- full K-layer
+propagation, six row gathers, ``bpr_loss_reg``, backward, dense Adam -- restated as
+
+  forward   K launches of the CSR SpMM, layer mean fused into the last        (a2)
+  bpr       one fused gather/dot/log-sigmoid/L2/scatter-add launch            (a4)
+  backward  K-1 Horner hops  acc <- g' + A acc  with the same SpMM kernel     (a3)
+  adam      fused into the epilogue of the K-th hop (dense grad never stored) (a5)
+
+on buffers that are allocated once, so a step is CUDA-graph capturable and nothing syncs
+with the host unless the caller reads the loss.  Evaluation is reference ``main.py:404-439``:
+one propagation, then fused score + mask + top-k and the hit / NDCG sums on the device.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import LgcnError
+
+
+def build_mask_csr(eval_users, train_user, train_item, num_users, device=None):
+    """Per-evaluated-user ascending train-item lists as CSR over the position in ``eval_users``
+    (what ``train_df.groupby('user_idx')['item_idx'].apply(list)`` feeds the mask loop of
+    reference ``main.py:407,422-424``).  Host numpy; returns int64 rowptr / int32 col tensors."""
+    tu = np.ascontiguousarray(train_user, np.int64)
+    ti = np.ascontiguousarray(train_item, np.int64)
+    order = np.lexsort((ti, tu))
+    tu, ti = tu[order], ti[order]
+    start = np.searchsorted(tu, np.arange(num_users + 1, dtype=np.int64))
+    eu = np.ascontiguousarray(eval_users, np.int64)
+    cnt = start[eu + 1] - start[eu]
+    rowptr = np.zeros(len(eu) + 1, np.int64)
+    np.cumsum(cnt, out=rowptr[1:])
+    src = np.repeat(start[eu] - rowptr[:-1], cnt) + np.arange(rowptr[-1], dtype=np.int64)
+    col = ti[src].astype(np.int32)
+    rp, cc = torch.from_numpy(rowptr), torch.from_numpy(col)
+    if device is not None:
+        rp, cc = rp.to(device), cc.to(device)
+    return rp, cc
+
+
+def xavier_uniform_table(rows_list, d, device, generator=None):
+    """users | items | brands block, each part ``nn.init.xavier_uniform_`` like reference
+    ``models/lightgcn.py:27-31`` (bound = sqrt(6/(rows+d)))."""
+    n = sum(rows_list)
+    block = torch.empty((n, d), dtype=torch.float32, device=device)
+    r = 0
+    for rows in rows_list:
+        bound = math.sqrt(6.0 / (rows + d)) if rows > 0 else 0.0
+        block[r:r + rows].uniform_(-bound, bound, generator=generator)
+        r += rows
+    return block
+
+
+class LightGCNEngine:
+    """Fused LightGCN step + full-rank evaluation on one GPU.
+
+    ``table``: the [N,d] users|items|brands parameter block (shared with the drop-in module
+    when created through ``LightGCN.engine``).  ``fusion``: optional dict(content=[I,c],
+    weight=[d,d+c], bias=[d]) enabling the ``LightGCN_Fusion`` item block (reference
+    ``models/lightgcn_fusion.py:45-49``); ``table`` then holds the raw id embeddings.
+    """
+
+    def __init__(self, g, num_users, num_items, num_brands, n_layers, table, lr=1e-3,
+                 weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, fusion=None, batch_size=2048):
+        self.g = g
+        self.U, self.I, self.B = int(num_users), int(num_items), int(num_brands)
+        self.N = self.U + self.I + self.B
+        self.K = int(n_layers)
+        if tuple(table.shape[:1]) != (self.N,) or not table.is_contiguous():
+            raise LgcnError("table must be a contiguous [num_users+num_items+num_brands, d] block")
+        if g.n_rows != self.N or g.n_cols != self.N:
+            raise LgcnError("graph size does not match the table")
+        self.P = table
+        self.d = int(table.shape[1])
+        self.dev = table.device
+        self.lr, self.lam, self.betas, self.eps = float(lr), float(weight_decay), betas, float(eps)
+        new = lambda: torch.empty((self.N, self.d), dtype=torch.float32, device=self.dev)  # noqa: E731
+        self.m = torch.zeros_like(self.P)
+        self.v = torch.zeros_like(self.P)
+        self.F = new()
+        self.work = [new() for _ in range(max(self.K - 1, 2 if self.K > 1 else 0))]
+        self.G1 = torch.zeros_like(self.P)          # g/(K+1): addend of every Horner hop
+        self.G2 = torch.zeros_like(self.P)          # regulariser grad (+ g/(K+1) w/o fusion)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.adam_scalars = torch.zeros(2, dtype=torch.float32, device=self.dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.bs = int(batch_size)
+        self._alloc_batch(self.bs)
+        self.fusion = None
+        if fusion is not None:
+            self._init_fusion(fusion)
+        self._graph = None
+        self.launches_per_step = self._count_launches()
+
+    # ---- setup ---------------------------------------------------------------------------
+    def _alloc_batch(self, bs):
+        self.bs = bs
+        self.b_users = torch.zeros(bs, dtype=torch.int64, device=self.dev)
+        self.b_pos = torch.zeros(bs, dtype=torch.int64, device=self.dev)
+        self.b_neg = torch.zeros(bs, dtype=torch.int64, device=self.dev)
+        self.sample_ws = torch.empty(2 * bs, dtype=torch.float32, device=self.dev)
+        self._graph = None
+
+    def _init_fusion(self, f):
+        C, W, b = f["content"], f["weight"], f["bias"]
+        if C.shape[0] != self.I or W.shape != (self.d, self.d + C.shape[1]) or b.shape != (self.d,):
+            raise LgcnError("fusion: shape mismatch")
+        z = torch.zeros_like
+        self.fusion = dict(C=C.contiguous(), W=W, b=b, mW=z(W), vW=z(W), mb=z(b), vb=z(b),
+                           gW=z(W), gb=z(b),
+                           g_eid=torch.empty((self.I, self.d), dtype=torch.float32, device=self.dev))
+        self.X0 = torch.empty((self.N, self.d), dtype=torch.float32, device=self.dev)
+
+    def _count_launches(self):
+        """Kernels of THIS library launched per training step (for bench.py's gpu_launches)."""
+        per_spmm = 3 if (self.g.long_row_threshold > 0 and self.g.n_long > 0) else 1
+        n = 2 * self.K * per_spmm + 2 + 1 + 1          # spmm fwd+bwd, bpr(+reduce), tick, zero
+        if self.fusion is not None:
+            n += 1 + 2 + 5                             # proj fwd, proj bwd (2), 5 adam launches
+        return n
+
+    # ---- pieces ----------------------------------------------------------------------------
+    def layer0(self):
+        """Input of the propagation: the table itself, or with the fused item block."""
+        if self.fusion is None:
+            return self.P
+        U, I = self.U, self.I
+        f = self.fusion
+        self.X0[:U].copy_(self.P[:U])
+        self.X0[U + I:].copy_(self.P[U + I:])
+        ops.fusion_proj_fwd(self.P[U:U + I], f["C"], f["W"], f["b"], out=self.X0[U:U + I])
+        return self.X0
+
+    def propagate(self):
+        """F = mean_k A^k E0 (reference ``models/lightgcn.py:44-54``); returns the [N,d] table."""
+        return ops.propagate(self.g, self.layer0(), self.K, out=self.F, work=self.work)
+
+    def forward(self):
+        """The reference's 5-tuple (``models/lightgcn.py:81``) as views, no autograd."""
+        F = self.propagate()
+        U, I = self.U, self.I
+        return F[:U], F[U:U + I], F[U + I:], self.P[:U], self.P[U:U + I]
+
+    def _step_body(self):
+        g, K, U, I = self.g, self.K, self.U, self.I
+        u, p, n = self.b_users, self.b_pos, self.b_neg
+        F = self.propagate()
+        nofus = self.fusion is None
+        ops.bpr_fused(F, self.P, u, p, n, U, self.lam, grad_scale=1.0 / (K + 1), gF=self.G1,
+                      gP=self.G2, gp_includes_gf=nofus, sample_ws=self.sample_ws,
+                      loss_out=self.loss)
+        ops.adam_tick(self.step_dev, self.adam_scalars, self.lr, self.betas)
+        acc = self.G1
+        hops = K - 1 if nofus else K
+        for k in range(hops):
+            acc = ops.spmm(g, acc, out=self.work[k % 2] if K > 1 else self.F, addend=self.G1)
+        if nofus:
+            ops.spmm_adam(g, acc, self.P, self.m, self.v, self.adam_scalars, addend=self.G2,
+                          betas=self.betas, eps=self.eps)
+        else:
+            f = self.fusion
+            f["gW"].zero_()
+            f["gb"].zero_()
+            ops.fusion_proj_bwd(self.P[U:U + I], f["C"], f["W"], self.X0[U:U + I], acc[U:U + I],
+                                g_eid=f["g_eid"], gW=f["gW"], gb=f["gb"])
+            kw = dict(betas=self.betas, eps=self.eps)
+            sc = self.adam_scalars
+            ops.adam(self.P[:U], acc[:U], self.m[:U], self.v[:U], sc, g1=self.G2[:U], **kw)
+            ops.adam(self.P[U:U + I], f["g_eid"], self.m[U:U + I], self.v[U:U + I], sc,
+                     g1=self.G2[U:U + I], **kw)
+            if self.B > 0:
+                ops.adam(self.P[U + I:], acc[U + I:], self.m[U + I:], self.v[U + I:], sc,
+                         g1=self.G2[U + I:], **kw)
+            ops.adam(f["W"], f["gW"], f["mW"], f["vW"], sc, **kw)
+            ops.adam(f["b"], f["gb"], f["mb"], f["vb"], sc, **kw)
+        ops.zero_rows(self.G1, self.G2, u, p, n, U)
+
+    # ---- public --------------------------------------------------------------------------
+    def capture(self):
+        """Capture one training step (static batch buffers) in a CUDA graph."""
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        saved = self._snapshot()
+        with torch.cuda.stream(s):
+            self._step_body()                       # warm-up outside capture
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self._restore(saved)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._step_body()
+        self._restore(saved)                        # capture does not execute, but be explicit
+        self._graph = graph
+        return graph
+
+    def _snapshot(self):
+        st = [self.P.clone(), self.m.clone(), self.v.clone(), self.step_dev.clone()]
+        if self.fusion is not None:
+            f = self.fusion
+            st += [f[k].clone() for k in ("W", "b", "mW", "vW", "mb", "vb")]
+        return st
+
+    def _restore(self, st):
+        self.P.copy_(st[0]); self.m.copy_(st[1]); self.v.copy_(st[2]); self.step_dev.copy_(st[3])
+        if self.fusion is not None:
+            f = self.fusion
+            for k, t in zip(("W", "b", "mW", "vW", "mb", "vb"), st[4:]):
+                f[k].copy_(t)
+
+    def bpr_step(self, users, pos, neg, use_graph=True):
+        """One fused training step on a (users, pos, neg) int64 batch (host or device tensors).
+        Returns the device loss tensor [1] (read it with ``.item()`` only when needed; reference
+        ``main.py:528`` syncs every step)."""
+        bs = users.numel()
+        if bs != self.bs:
+            self._alloc_batch(bs)
+        self.b_users.copy_(users, non_blocking=True)
+        self.b_pos.copy_(pos, non_blocking=True)
+        self.b_neg.copy_(neg, non_blocking=True)
+        if use_graph:
+            if self._graph is None:
+                self.capture()
+            self._graph.replay()
+        else:
+            self._step_body()
+        return self.loss
+
+    def bpr_loss(self, users, pos, neg):
+        """Loss only (no gradient, no update) on the current parameters."""
+        F = self.propagate()
+        return ops.bpr_fused(F, self.P, users, pos, neg, self.U, self.lam)
+
+    def rate_topk(self, users, mask_rowptr=None, mask_col=None, k=20, propagate=True):
+        """Full-rank top-k item ids for ``users`` with their train items excluded (reference
+        ``main.py:413-426``)."""
+        F = self.propagate() if propagate else self.F
+        return ops.score_topk(F[:self.U], F[self.U:self.U + self.I], users, mask_rowptr, mask_col, k)
+
+    def evaluate(self, eval_users, targets, mask_rowptr, mask_col, k=20, batch_users=None):
+        """recall@k / NDCG@k as reference ``main.py:404-439``.  Returns (recall, ndcg, ids)."""
+        self.propagate()
+        nu = eval_users.numel()
+        sums = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        ids, _ = self.rate_topk(eval_users, mask_rowptr, mask_col, k, propagate=False)
+        ops.eval_metrics(ids, targets, sums)
+        s = sums.cpu().numpy()
+        return float(s[0] / nu), float(s[1] / nu), ids

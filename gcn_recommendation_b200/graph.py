@@ -1,0 +1,189 @@
+"""Normalised adjacency in CSR form, resident in HBM.
+
+Host-side mirror of the reference's adjacency builder (reference ``main.py:283-336``) and the
+adapter that turns the ``torch.sparse_coo`` tensor ``main.py`` passes to ``forward``
+(``main.py:334-336,495``) into the CSR the kernels use.
+
+Layout in HBM (one graph): ``rowptr`` int32[N+1], ``col`` int32[nnz] (ascending inside a row),
+``val`` fp32[nnz] = fl32(fl32(d_r*m)*d_c), plus the long-row plan (rows longer than
+``long_row_threshold`` are cut into ``seg_len`` segments, include/lgcn.h).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+LONG_ROW_THRESHOLD = 1024
+SEG_LEN = 512
+
+
+class NormAdjCSR:
+    """D^-1/2 A D^-1/2 as CSR on one GPU (rows ``[row_begin, row_begin+n_rows)`` of an
+    ``n_cols``-node graph; the whole graph when not sharded)."""
+
+    def __init__(self, rowptr, col, val, n_cols, row_begin=0, long_row_threshold=LONG_ROW_THRESHOLD,
+                 seg_len=SEG_LEN, rowptr_host=None):
+        self.rowptr, self.col, self.val = rowptr, col, val
+        self.n_rows = int(rowptr.numel() - 1)
+        self.n_cols = int(n_cols)
+        self.row_begin = int(row_begin)
+        self.nnz = int(col.numel())
+        self.device = rowptr.device
+        self._seg_ws = {}
+        self._plan_long_rows(long_row_threshold, seg_len, rowptr_host)
+
+    # ---- long-row plan (host logic, once per graph) ------------------------------------
+    def _plan_long_rows(self, threshold, seg_len, rowptr_host=None):
+        self.long_row_threshold = int(threshold)
+        self.seg_len = int(seg_len)
+        self.n_long = 0
+        self.n_seg = 0
+        self.long_row_ids = None
+        self.long_seg_ptr = None
+        if threshold <= 0 or self.n_rows == 0:
+            self.long_row_threshold = 0
+            return
+        rp = rowptr_host if rowptr_host is not None else self.rowptr.cpu().numpy()
+        deg = np.diff(rp.astype(np.int64))
+        long_ids = np.nonzero(deg > threshold)[0].astype(np.int32)
+        if len(long_ids) == 0:
+            return
+        nseg = (deg[long_ids] + seg_len - 1) // seg_len
+        seg_ptr = np.zeros(len(long_ids) + 1, np.int32)
+        np.cumsum(nseg, out=seg_ptr[1:])
+        self.n_long = int(len(long_ids))
+        self.n_seg = int(seg_ptr[-1])
+        self.long_row_ids = torch.from_numpy(long_ids).to(self.device)
+        self.long_seg_ptr = torch.from_numpy(seg_ptr).to(self.device)
+
+    def seg_ws(self, d):
+        if self.n_seg == 0:
+            return None
+        ws = self._seg_ws.get(d)
+        if ws is None:
+            ws = torch.empty((self.n_seg, d), dtype=torch.float32, device=self.device)
+            self._seg_ws[d] = ws
+        return ws
+
+    def degrees_host(self):
+        return np.diff(self.rowptr.cpu().numpy().astype(np.int64))
+
+    # ---- builders ------------------------------------------------------------------------
+    @classmethod
+    def from_interactions(cls, train_user, train_item, num_users, num_items, num_brands, device,
+                          item_brand=None, **kw):
+        """Build from the training interactions exactly as reference ``main.py:283-336`` does:
+        symmetric COO of ones over users|items|brands (``:304-313``), duplicates summed by the
+        CSR conversion, ``d = np.power(rowsum, -0.5)`` in fp32 with inf -> 0 (``:326-329``) --
+        the SAME numpy call on the host so the weights are bit-equal -- and the product
+        ``fl32(fl32(d_r*m)*d_c)`` (``:330-331``) formed on the GPU by ``lgcn_edge_weights``."""
+        U, I, B = int(num_users), int(num_items), int(num_brands)
+        N = U + I + B
+        u = np.ascontiguousarray(train_user, dtype=np.int64)
+        it = np.ascontiguousarray(train_item, dtype=np.int64) + U
+        if len(u) and (u.min() < 0 or u.max() >= U or it.min() < U or it.max() >= U + I):
+            raise ValueError("interaction index out of range")
+        rows, cols = [u, it], [it, u]
+        if item_brand is not None:
+            ib_i = np.ascontiguousarray(item_brand[0], dtype=np.int64) + U
+            ib_b = np.ascontiguousarray(item_brand[1], dtype=np.int64) + U + I
+            rows += [ib_i, ib_b]
+            cols += [ib_b, ib_i]
+        key = np.concatenate(rows) * N + np.concatenate(cols)
+        del rows, cols
+        key.sort()
+        if len(key):
+            first = np.ones(len(key), dtype=bool)
+            first[1:] = key[1:] != key[:-1]
+            ukey = key[first]
+            pos = np.flatnonzero(first)
+            mult = np.diff(np.append(pos, len(key))).astype(np.float32)
+        else:
+            ukey, mult = key, np.zeros(0, np.float32)
+        del key
+        r = ukey // N
+        c = (ukey - r * N).astype(np.int32)
+        counts = np.bincount(r, minlength=N)
+        rowptr = np.zeros(N + 1, np.int64)
+        np.cumsum(counts, out=rowptr[1:])
+        if rowptr[-1] >= 2 ** 31:
+            raise ValueError("nnz does not fit int32")
+        unit = bool(len(mult) == 0 or mult.max() == 1.0)
+        deg = (counts if unit else np.bincount(r, weights=mult, minlength=N)).astype(np.float32)
+        with np.errstate(divide="ignore"):
+            dinv = np.power(deg, np.float32(-0.5)).astype(np.float32)   # main.py:328
+        dinv[np.isinf(dinv)] = 0.0                                       # main.py:329
+        rp32 = rowptr.astype(np.int32)
+        t_rowptr = torch.from_numpy(rp32).to(device)
+        t_col = torch.from_numpy(c).to(device)
+        t_dinv = torch.from_numpy(dinv).to(device)
+        t_mult = None if unit else torch.from_numpy(mult).to(device)
+        t_val = torch.empty(len(c), dtype=torch.float32, device=device)
+        lib = _lib.load()
+        _lib.check(lib.lgcn_edge_weights(_lib.ptr(t_rowptr, "i32"), _lib.ptr(t_col, "i32"),
+                                         _lib.ptr(t_dinv), _lib.ptr(t_mult, allow_none=True),
+                                         _lib.ptr(t_val), N, _lib.stream_ptr(device)))
+        g = cls(t_rowptr, t_col, t_val, N, rowptr_host=rp32, **kw)
+        g.dinv = t_dinv
+        return g
+
+    @classmethod
+    def from_sparse_coo(cls, adj_mat, **kw):
+        """Adapter for the uncoalesced fp32 ``torch.sparse_coo`` tensor of reference
+        ``main.py:334-336``.  It is row-major sorted with unique entries (it came out of a scipy
+        CSR); that is verified on the device, and anything else is coalesced (sorted, duplicates
+        summed -- what ``torch.sparse.mm`` itself would do) first."""
+        if adj_mat.layout != torch.sparse_coo:
+            raise TypeError("adj_mat must be a torch.sparse_coo tensor")
+        if not adj_mat.is_cuda:
+            raise _lib.LgcnError("adj_mat must live on a CUDA device (no CPU fallback)")
+        N = adj_mat.shape[0]
+        lib = _lib.load()
+        for attempt in range(2):
+            idx = adj_mat._indices()
+            vals = adj_mat._values()
+            if vals.dtype != torch.float32:
+                raise TypeError("adjacency values must be float32")
+            row = idx[0].contiguous()
+            colin = idx[1].contiguous()
+            nnz = int(vals.numel())
+            rowptr = torch.empty(N + 1, dtype=torch.int32, device=adj_mat.device)
+            col = torch.empty(nnz, dtype=torch.int32, device=adj_mat.device)
+            status = torch.zeros(1, dtype=torch.int32, device=adj_mat.device)
+            _lib.check(lib.lgcn_csr_from_sorted_coo(_lib.ptr(row, "i64"), _lib.ptr(colin, "i64"), nnz,
+                                                    N, _lib.ptr(rowptr, "i32"), _lib.ptr(col, "i32"),
+                                                    _lib.ptr(status, "i32"),
+                                                    _lib.stream_ptr(adj_mat.device)))
+            if int(status.item()) == 0:
+                return cls(rowptr, col, vals.contiguous().clone(), adj_mat.shape[1], **kw)
+            if attempt == 0:
+                adj_mat = adj_mat.coalesce()
+        raise _lib.LgcnError("adjacency indices are out of range")
+
+    def row_shard(self, row_begin, row_end):
+        """CSR of rows [row_begin, row_end) (columns stay global) for row-sharded propagation."""
+        rp = self.rowptr[row_begin:row_end + 1]
+        e0, e1 = int(rp[0].item()), int(rp[-1].item())
+        return NormAdjCSR((rp - e0).contiguous(), self.col[e0:e1].contiguous(),
+                          self.val[e0:e1].contiguous(), self.n_cols, row_begin=row_begin,
+                          long_row_threshold=self.long_row_threshold or 0, seg_len=self.seg_len)
+
+
+_COO_CACHE = {}
+
+
+def csr_for(adj_mat):
+    """CSR for the ``adj_mat`` object ``main.py`` passes on every call (``main.py:495,413``),
+    converted once and cached on the identity of its index / value storage."""
+    key = (adj_mat._indices().data_ptr(), adj_mat._values().data_ptr(), int(adj_mat._nnz()),
+           tuple(adj_mat.shape), str(adj_mat.device))
+    g = _COO_CACHE.get(key)
+    if g is None:
+        if len(_COO_CACHE) > 8:
+            _COO_CACHE.clear()
+        g = NormAdjCSR.from_sparse_coo(adj_mat)
+        g._keepalive = adj_mat          # the key is only valid while the tensor lives
+        _COO_CACHE[key] = g
+    return g

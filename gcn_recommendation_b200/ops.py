@@ -1,0 +1,255 @@
+"""Host-side operators over the C ABI (include/lgcn.h): one Python call per kernel entry point
+and the ``torch.autograd.Function``s the drop-in models use.
+
+Everything here launches hand-written sm_100a kernels; there is no eager/PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import SPMM_ADAM, SPMM_ADD, SPMM_MEAN, SPMM_PLAIN, SpmmArgs, check, ptr, stream_ptr
+
+
+def _spmm_args(g, x, mode, d):
+    a = SpmmArgs()
+    a.rowptr, a.col, a.val = ptr(g.rowptr, "i32"), ptr(g.col, "i32"), ptr(g.val)
+    a.x = ptr(x)
+    a.n_rows, a.d, a.mode = g.n_rows, d, mode
+    if g.long_row_threshold > 0 and g.n_long > 0:
+        a.long_row_threshold = g.long_row_threshold
+        a.n_long = g.n_long
+        a.long_row_ids = ptr(g.long_row_ids, "i32")
+        a.long_seg_ptr = ptr(g.long_seg_ptr, "i32")
+        a.seg_len, a.n_seg = g.seg_len, g.n_seg
+        a.seg_ws = ptr(g.seg_ws(d))
+    return a
+
+
+def _check_table(t, rows, d, name):
+    if t.dim() != 2 or t.shape[0] < rows or t.shape[1] != d:
+        raise _lib.LgcnError(f"{name}: expected at least [{rows},{d}], got {tuple(t.shape)}")
+
+
+def spmm(g, x, out=None, addend=None, mean_layers=None):
+    """out = A_hat x  (+ addend)  |  mean over [*mean_layers, A_hat x] (reference
+    ``models/lightgcn.py:45,54``).  ``g``: :class:`graph.NormAdjCSR`; ``x`` [n_cols, d]."""
+    d = x.shape[1]
+    _check_table(x, g.n_cols, d, "x")
+    if out is None:
+        out = torch.empty((g.n_rows, d), dtype=torch.float32, device=x.device)
+    _check_table(out, g.n_rows, d, "out")
+    if out.data_ptr() == x.data_ptr():
+        raise _lib.LgcnError("spmm cannot run in place")
+    if mean_layers is not None:
+        a = _spmm_args(g, x, SPMM_MEAN, d)
+        if not 1 <= len(mean_layers) <= 8:
+            raise _lib.LgcnError("mean epilogue supports 1..8 earlier layers")
+        for i, l in enumerate(mean_layers):
+            _check_table(l, g.n_rows, d, "layer")
+            a.layers[i] = ptr(l)
+        a.n_layers = len(mean_layers)
+    elif addend is not None:
+        _check_table(addend, g.n_rows, d, "addend")
+        a = _spmm_args(g, x, SPMM_ADD, d)
+        a.addend = ptr(addend)
+    else:
+        a = _spmm_args(g, x, SPMM_PLAIN, d)
+    a.y = ptr(out)
+    check(_lib.load().lgcn_spmm(ctypes.byref(a), stream_ptr(x.device)))
+    return out
+
+
+def spmm_adam(g, x, p, m, v, adam_scalars, addend=None, addend2=None, betas=(0.9, 0.999),
+              eps=1e-8, g_out=None):
+    """Last backward hop fused with Adam: grad = addend + A_hat x + addend2; Adam(p, m, v, grad)
+    (reference ``main.py:525-526``)."""
+    d = x.shape[1]
+    a = _spmm_args(g, x, SPMM_ADAM, d)
+    for t, n in ((p, "p"), (m, "m"), (v, "v")):
+        _check_table(t, g.n_rows, d, n)
+    a.p, a.m, a.v = ptr(p), ptr(m), ptr(v)
+    a.addend = ptr(addend, allow_none=True)
+    a.addend2 = ptr(addend2, allow_none=True)
+    a.adam_scalars = ptr(adam_scalars)
+    a.beta1, a.beta2, a.eps = betas[0], betas[1], eps
+    a.g_out = ptr(g_out, allow_none=True)
+    check(_lib.load().lgcn_spmm(ctypes.byref(a), stream_ptr(x.device)))
+
+
+def propagate(g, e0, n_layers, out=None, work=None):
+    """K-layer propagation with the layer mean fused into the last SpMM (reference
+    ``models/lightgcn.py:44-54``).  Returns F [N,d].  ``work``: optional list of K-1 scratch
+    tables (E_1..E_{K-1})."""
+    if n_layers < 1:
+        raise _lib.LgcnError("n_layers must be >= 1")
+    layers = [e0]
+    for k in range(n_layers - 1):
+        buf = work[k] if work is not None else None
+        layers.append(spmm(g, layers[-1], out=buf))
+    return spmm(g, layers[-1], out=out, mean_layers=layers)
+
+
+def propagate_backward(g, grad_f, n_layers, work=None):
+    """dL/dE0 = sum_k A^k g/(K+1) as Horner hops acc <- g' + A acc (A symmetric), the
+    autograd of reference ``models/lightgcn.py:44-54``."""
+    g1 = grad_f * (1.0 / (n_layers + 1))
+    acc = g1
+    for k in range(n_layers):
+        buf = work[k % 2] if work is not None else None
+        acc = spmm(g, acc, out=buf, addend=g1)
+    return acc
+
+
+def bpr_fused(F, P, users, pos, neg, num_users, lam, grad_scale=1.0, gF=None, gP=None,
+              gp_includes_gf=False, sample_ws=None, loss_out=None):
+    """Fused gather + BPR + L2 + scatter-add (reference ``main.py:366-402,496-497``)."""
+    bs = users.numel()
+    d = F.shape[1]
+    dev = F.device
+    if sample_ws is None:
+        sample_ws = torch.empty(2 * bs, dtype=torch.float32, device=dev)
+    if loss_out is None:
+        loss_out = torch.empty(1, dtype=torch.float32, device=dev)
+    flags = 0
+    if gF is None and gP is None:
+        flags |= _lib.BPR_NO_GRAD
+    if gp_includes_gf:
+        flags |= _lib.BPR_GP_INCLUDES_GF
+    check(_lib.load().lgcn_bpr_fused(ptr(F), ptr(P), ptr(users, "i64"), ptr(pos, "i64"),
+                                     ptr(neg, "i64"), bs, d, num_users, lam, grad_scale, flags,
+                                     ptr(sample_ws), ptr(loss_out), ptr(gF, allow_none=True),
+                                     ptr(gP, allow_none=True), stream_ptr(dev)))
+    return loss_out
+
+
+def zero_rows(t0, t1, users, pos, neg, num_users):
+    d = t0.shape[1]
+    check(_lib.load().lgcn_zero_rows(ptr(t0), ptr(t1, allow_none=True), ptr(users, "i64"),
+                                     ptr(pos, "i64"), ptr(neg, "i64"), users.numel(), d, num_users,
+                                     stream_ptr(t0.device)))
+
+
+def adam_tick(step_dev, scalars, lr, betas=(0.9, 0.999)):
+    check(_lib.load().lgcn_adam_tick(ptr(step_dev, "i64"), ptr(scalars), lr, betas[0], betas[1],
+                                     stream_ptr(scalars.device)))
+
+
+def adam(p, g0, m, v, scalars, g1=None, betas=(0.9, 0.999), eps=1e-8):
+    check(_lib.load().lgcn_adam(ptr(p), ptr(g0), ptr(g1, allow_none=True), ptr(m), ptr(v),
+                                p.numel(), ptr(scalars), betas[0], betas[1], eps,
+                                stream_ptr(p.device)))
+
+
+def fusion_proj_fwd(e_id, content, W, b, out=None):
+    """leaky_relu([E_id | C] W^T + b) without the concat (reference
+    ``models/lightgcn_fusion.py:45-49``)."""
+    n, d = e_id.shape
+    c = content.shape[1]
+    if W.shape != (d, d + c) or b.shape != (d,) or content.shape[0] != n:
+        raise _lib.LgcnError("fusion_proj: shape mismatch")
+    if out is None:
+        out = torch.empty((n, d), dtype=torch.float32, device=e_id.device)
+    check(_lib.load().lgcn_fusion_proj_fwd(ptr(e_id), ptr(content), ptr(W), ptr(b), n, d, c,
+                                           ptr(out), stream_ptr(e_id.device)))
+    return out
+
+
+def fusion_proj_bwd(e_id, content, W, H, gH, g_eid=None, gW=None, gb=None):
+    n, d = e_id.shape
+    c = content.shape[1]
+    dev = e_id.device
+    if g_eid is None:
+        g_eid = torch.empty((n, d), dtype=torch.float32, device=dev)
+    if gW is None:
+        gW = torch.zeros((d, d + c), dtype=torch.float32, device=dev)
+    if gb is None:
+        gb = torch.zeros((d,), dtype=torch.float32, device=dev)
+    check(_lib.load().lgcn_fusion_proj_bwd(ptr(e_id), ptr(content), ptr(W), ptr(H), ptr(gH), n, d,
+                                           c, ptr(g_eid), ptr(gW), ptr(gb), stream_ptr(dev)))
+    return g_eid, gW, gb
+
+
+def score_topk(F_user, F_item, users, mask_rowptr=None, mask_col=None, k=20):
+    """Full-rank scores + train mask + top-k (reference ``main.py:420-426``).
+    Returns (ids int32 [nu,k], scores fp32 [nu,k])."""
+    nu = users.numel()
+    d = F_user.shape[1]
+    dev = F_user.device
+    ids = torch.empty((nu, k), dtype=torch.int32, device=dev)
+    sc = torch.empty((nu, k), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    wsb = lib.lgcn_score_topk_workspace(nu, F_item.shape[0], d, k)
+    ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+    check(lib.lgcn_score_topk(ptr(F_user), ptr(F_item), ptr(users, "i64"), nu, F_item.shape[0], d,
+                              ptr(mask_rowptr, "i64", allow_none=True),
+                              ptr(mask_col, "i32", allow_none=True), k, ptr(ids, "i32"), ptr(sc),
+                              ws.data_ptr(), wsb, stream_ptr(dev)))
+    return ids, sc
+
+
+def eval_metrics(topk_ids, targets, sums=None):
+    """sums += [#hits, sum 1/log2(rank+2)] (reference ``main.py:430-438``)."""
+    nu, k = topk_ids.shape
+    if sums is None:
+        sums = torch.zeros(2, dtype=torch.float64, device=topk_ids.device)
+    check(_lib.load().lgcn_eval_metrics(ptr(topk_ids, "i32"), ptr(targets, "i64"), nu, k,
+                                        ptr(sums, "f64"), stream_ptr(topk_ids.device)))
+    return sums
+
+
+# ------------------------------------------------------------------------------------------
+# autograd glue for the drop-in models (main.py keeps its own loss / optimizer there)
+# ------------------------------------------------------------------------------------------
+class PropagateFunction(torch.autograd.Function):
+    """F = mean_k A^k E0 with E0 = cat(tables) (reference ``models/lightgcn.py:37-59``)."""
+
+    @staticmethod
+    def forward(ctx, g, n_layers, *tables):
+        e0 = _as_block(tables)
+        ctx.g, ctx.n_layers = g, n_layers
+        ctx.sizes = [t.shape[0] for t in tables]
+        return propagate(g, e0, n_layers)
+
+    @staticmethod
+    def backward(ctx, grad_f):
+        acc = propagate_backward(ctx.g, grad_f.contiguous(), ctx.n_layers)
+        return (None, None) + tuple(torch.split(acc, ctx.sizes, dim=0))
+
+
+def _as_block(tables):
+    """Zero-copy [N,d] view when the tables are consecutive slices of one allocation
+    (models/_packing.py arranges that), else one concat (reference ``lightgcn.py:40``)."""
+    t0 = tables[0]
+    d = t0.shape[1]
+    ok = all(t.is_contiguous() and t.shape[1] == d and t.dtype == torch.float32 for t in tables)
+    if ok:
+        end = t0.data_ptr()
+        for t in tables:
+            if t.data_ptr() != end or t.untyped_storage().data_ptr() != t0.untyped_storage().data_ptr():
+                ok = False
+                break
+            end += t.numel() * 4
+    if ok:
+        n = sum(t.shape[0] for t in tables)
+        return t0.detach().as_strided((n, d), (d, 1))
+    return torch.cat([t.detach() for t in tables], dim=0)
+
+
+class FusionProjFunction(torch.autograd.Function):
+    """H = leaky_relu([E_id | C] W^T + b) (reference ``models/lightgcn_fusion.py:45-49``)."""
+
+    @staticmethod
+    def forward(ctx, e_id, content, W, b):
+        e_id_c, W_c, b_c = e_id.detach().contiguous(), W.detach().contiguous(), b.detach().contiguous()
+        H = fusion_proj_fwd(e_id_c, content, W_c, b_c)
+        ctx.save_for_backward(e_id_c, content, W_c, H)
+        return H
+
+    @staticmethod
+    def backward(ctx, gH):
+        e_id, content, W, H = ctx.saved_tensors
+        g_eid, gW, gb = fusion_proj_bwd(e_id, content, W, H, gH.contiguous())
+        return g_eid, None, gW, gb

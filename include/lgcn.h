@@ -1,0 +1,189 @@
+/*
+ * lgcn.h -- C ABI of the B200-native LightGCN hot path (liblgcn_b200.so).
+ *
+ * The reference (Validation-m3sSAGE/GCN_Recommendation) is pure Python and has no FFI of
+ * its own: its hot path is a chain of PyTorch / SciPy library calls.  Every entry point
+ * below replaces one of those call sites (cited as reference file:line) and is what a
+ * maintainer binds with ctypes from the reference's model plugin.
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a BORROWED DEVICE pointer unless it is named
+ *    *_host; the library never allocates, frees, synchronises or throws.
+ *  - every call takes the cudaStream_t to launch on (pass torch's current stream).
+ *  - return value: 0 on success, a positive cudaError_t if a launch failed, or a negative
+ *    LGCN_E_* code for an argument the kernels do not support.
+ *  - fp32 everywhere; row-major tables [rows, d]; d in {16,32,64,128,256}; 16-byte aligned.
+ *  - a "table" is the concatenation users | items | brands (reference models/lightgcn.py:40).
+ */
+#ifndef LGCN_H
+#define LGCN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *lgcn_stream_t; /* == cudaStream_t */
+
+#if defined(__GNUC__)
+#define LGCN_API __attribute__((visibility("default")))
+#else
+#define LGCN_API
+#endif
+
+#define LGCN_ABI_VERSION 1
+
+#define LGCN_E_BAD_DIM   (-1) /* embedding dim not supported              */
+#define LGCN_E_BAD_ARG   (-2) /* null pointer / negative size / bad mode  */
+#define LGCN_E_TOO_LARGE (-3) /* size exceeds an int32 index limit        */
+
+LGCN_API int lgcn_abi_version(void);
+/* human readable text for a return code of this library (static storage) */
+LGCN_API const char *lgcn_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------
+ * a1  Graph: COO -> CSR and symmetric normalisation.
+ * Replaces: scipy coo->csr + D^-1/2 A D^-1/2 (reference main.py:321-331) and the COO tensor
+ * torch.sparse.mm re-sorts on every call (reference main.py:334-336, models/lightgcn.py:45).
+ * ------------------------------------------------------------------------------------- */
+
+/* Row-major sorted COO (what main.py:334-336 hands to forward) -> CSR.
+ * rowptr[n_rows+1], col[nnz] int32.  status[0] receives the number of adjacent pairs that
+ * violate strict (row,col) ordering (0 == valid CSR order, no duplicates). */
+LGCN_API int lgcn_csr_from_sorted_coo(const int64_t *coo_row, const int64_t *coo_col, int64_t nnz,
+                             int64_t n_rows, int32_t *rowptr, int32_t *col, int32_t *status,
+                             lgcn_stream_t stream);
+
+/* val[e] = fl32(fl32(dinv[row]*mult[e]) * dinv[col[e]])  (mult == NULL -> 1), the value
+ * scipy produces at main.py:330-331.  dinv is computed by the caller with the same
+ * np.power(fp32, -0.5) call as main.py:328 so that the weights are bit-equal. */
+LGCN_API int lgcn_edge_weights(const int32_t *rowptr, const int32_t *col, const float *dinv,
+                      const float *mult, float *val, int64_t n_rows, lgcn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a2/a3/a5  Normalised-adjacency SpMM with fused epilogues.
+ * Replaces: torch.sparse.mm (reference models/lightgcn.py:45, lightgcn_fusion.py:56), its
+ * autograd backward, torch.mean(torch.stack()) (lightgcn.py:54) and optimizer.step()
+ * (main.py:526) when fused into the last backward hop.
+ *
+ * y[r,:] = sum_e val[e] * X[col[e],:]  for local rows r in [0,n_rows): rowptr is the CSR of
+ * those rows, col indexes rows of X (the full table), every epilogue array is indexed by the
+ * LOCAL row.  Rows no longer than the long-row threshold are accumulated as a sequential fp32
+ * FMA in ascending column order (bit-equal to the CPU reference); longer rows are split into
+ * segments that are summed in a fixed order (deterministic, not bit-equal).
+ * ------------------------------------------------------------------------------------- */
+typedef struct lgcn_spmm_args {
+    const int32_t *rowptr;      /* [n_rows+1]                                         */
+    const int32_t *col;         /* [nnz]                                              */
+    const float   *val;         /* [nnz]                                              */
+    const float   *x;           /* [*, d] gathered table                              */
+    int64_t        n_rows;
+    int32_t        d;
+    int32_t        mode;        /* LGCN_SPMM_*                                        */
+    float         *y;           /* [n_rows,d] output (modes PLAIN, ADD, MEAN)         */
+    const float   *addend;      /* ADD, ADAM: y = addend + A x ; may be NULL in ADAM  */
+    const float   *layers[8];   /* MEAN: earlier layers E_0..E_{n-1} (local rows)     */
+    int32_t        n_layers;    /* MEAN: number of entries in layers                  */
+    /* long-row plan (host-built once per graph, see graph.py): rows with more than
+     * long_row_threshold entries are cut into segments of seg_len entries, one sub-warp
+     * per segment, partial sums staged in seg_ws and combined in segment order.
+     * long_row_threshold == 0 disables the plan (every row sequential).               */
+    int32_t        long_row_threshold;
+    int32_t        n_long;      /* number of long rows                                */
+    const int32_t *long_row_ids;/* [n_long] local row ids, ascending                  */
+    const int32_t *long_seg_ptr;/* [n_long+1] first segment of each long row          */
+    int32_t        seg_len;     /* entries per segment                                */
+    int32_t        n_seg;       /* total segments == long_seg_ptr[n_long] (host copy) */
+    float         *seg_ws;      /* [long_seg_ptr[n_long], d] scratch                  */
+    /* ADAM: g = addend + A x (+ addend2) is consumed by a dense Adam update of p       */
+    const float   *addend2;     /* optional second addend (regulariser gradient)      */
+    float         *p, *m, *v;   /* [n_rows,d] parameters and Adam moments             */
+    const float   *adam_scalars;/* device [2]: step_size=lr/(1-b1^t), sqrt(1-b2^t)    */
+    float          beta1, beta2, eps;
+    float         *g_out;       /* ADAM: optional [n_rows,d] copy of g (NULL = none)  */
+} lgcn_spmm_args;
+
+#define LGCN_SPMM_PLAIN 0 /* y = A x                                                    */
+#define LGCN_SPMM_ADD   1 /* y = addend + A x              (Horner backward hop)        */
+#define LGCN_SPMM_MEAN  2 /* y = (E_0 + ... + E_{n-1} + A x) / (n+1), sequential sum then
+                             a true division (reference models/lightgcn.py:54)          */
+#define LGCN_SPMM_ADAM  3 /* g = addend + A x + addend2 ; Adam(p,m,v,g)                 */
+
+LGCN_API int lgcn_spmm(const lgcn_spmm_args *args_host, lgcn_stream_t stream);
+/* sizeof(lgcn_spmm_args) as compiled, so that a binding can verify its struct layout */
+LGCN_API size_t lgcn_sizeof_spmm_args(void);
+
+/* ---------------------------------------------------------------------------------------
+ * a4  Fused BPR + L2 step.
+ * Replaces: the six row gathers (reference main.py:496-497), bpr_loss_reg (main.py:366-402)
+ * and their autograd backward (index_put accumulate).
+ *   x_s   = <F[u_s], F[io+p_s]> - <F[u_s], F[io+n_s]>
+ *   loss  = -mean_s log(sigmoid(x_s)+1e-8) + lam*sum_s(|P[u_s]|^2+|P[io+p_s]|^2+|P[io+n_s]|^2)/bs
+ *   gF   += grad_scale * dloss/dF            (rows u, io+p, io+n; float atomics)
+ *   gP   += dloss/dP through the regulariser (2*lam/bs * row, once per occurrence)
+ *           (+ the gF contribution too when LGCN_BPR_GP_INCLUDES_GF is set)
+ * F: [N,d] propagated table; P: [N,d] layer-0 id table (the 4th/5th forward outputs);
+ * io = item_offset = num_users.  sample_ws: [2*bs] floats of scratch.  loss_out: [1].
+ * ------------------------------------------------------------------------------------- */
+#define LGCN_BPR_GP_INCLUDES_GF 1
+#define LGCN_BPR_NO_GRAD        2 /* loss only */
+
+LGCN_API int lgcn_bpr_fused(const float *F, const float *P, const int64_t *users, const int64_t *pos,
+                   const int64_t *neg, int64_t bs, int32_t d, int64_t item_offset, float lam,
+                   float grad_scale, int32_t flags, float *sample_ws, float *loss_out,
+                   float *gF, float *gP, lgcn_stream_t stream);
+
+/* zero the rows {u_s, io+p_s, io+n_s} of up to two [N,d] tables (undo of the scatter) */
+LGCN_API int lgcn_zero_rows(float *t0, float *t1, const int64_t *users, const int64_t *pos,
+                   const int64_t *neg, int64_t bs, int32_t d, int64_t item_offset,
+                   lgcn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a5  Dense Adam (torch.optim.Adam defaults, reference main.py:469,526).
+ * lgcn_adam_tick: t += 1 on the device and refresh adam_scalars = {lr/(1-b1^t),
+ * sqrt(1-b2^t)} (step counter and scalars stay on the device so a step is graph-capturable).
+ * lgcn_adam: g = g0 (+ g1); m,v,p updated in place.
+ * ------------------------------------------------------------------------------------- */
+LGCN_API int lgcn_adam_tick(int64_t *step_dev, float *adam_scalars, float lr, float beta1, float beta2,
+                   lgcn_stream_t stream);
+LGCN_API int lgcn_adam(float *p, const float *g0, const float *g1, float *m, float *v, int64_t n,
+              const float *adam_scalars, float beta1, float beta2, float eps,
+              lgcn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a6  Fusion item block (reference models/lightgcn_fusion.py:45-49).
+ *   H = leaky_relu([E_id | C] W^T + b, 0.01)      W: [d, d+c] row-major (nn.Linear.weight)
+ * The concatenation is never materialised.  Backward: gH is the gradient w.r.t. H;
+ * gEid [n_items,d] is overwritten; gW [d,d+c] and gb [d] are ACCUMULATED (caller zeroes).
+ * ------------------------------------------------------------------------------------- */
+LGCN_API int lgcn_fusion_proj_fwd(const float *Eid, const float *C, const float *W, const float *b,
+                         int64_t n_items, int32_t d, int32_t c, float *H,
+                         lgcn_stream_t stream);
+LGCN_API int lgcn_fusion_proj_bwd(const float *Eid, const float *C, const float *W, const float *H,
+                         const float *gH, int64_t n_items, int32_t d, int32_t c, float *gEid,
+                         float *gW, float *gb, lgcn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a7  Full-rank rating: scores + train-item mask + top-k, scores never reach HBM.
+ * Replaces: torch.matmul (reference main.py:420), the per-user mask loop (main.py:422-424)
+ * and torch.topk (main.py:426).
+ *   score(q,i) = <Fu[users[q]], Fi[i]>  (fp32, sequential FMA over the feature index)
+ *   items in mask row q (CSR over query position, ascending item ids) are excluded
+ *   out_ids/out_scores [nu,k]: descending score, ties -> lower item id first.
+ * k <= 32.  workspace: lgcn_score_topk_workspace() bytes.
+ * lgcn_eval_metrics: sums[0] += #hits, sums[1] += sum 1/log2(rank+2) (main.py:430-438).
+ * ------------------------------------------------------------------------------------- */
+LGCN_API size_t lgcn_score_topk_workspace(int64_t nu, int64_t n_items, int32_t d, int32_t k);
+LGCN_API int lgcn_score_topk(const float *Fu, const float *Fi, const int64_t *users, int64_t nu,
+                    int64_t n_items, int32_t d, const int64_t *mask_rowptr,
+                    const int32_t *mask_col, int32_t k, int32_t *out_ids, float *out_scores,
+                    void *workspace, size_t workspace_bytes, lgcn_stream_t stream);
+LGCN_API int lgcn_eval_metrics(const int32_t *topk_ids, const int64_t *targets, int64_t nu, int32_t k,
+                      double *sums, lgcn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGCN_H */

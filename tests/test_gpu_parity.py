@@ -1,0 +1,403 @@
+"""GPU parity tests: the sm_100a kernels (through the C ABI) against the CPU oracle and the
+golden vectors produced by the reference itself.
+
+Bars (BASELINE.json north_star): bit-exact CSR construction / normalisation / top-k ids,
+<= 1e-5 relative (fp32) for propagated embeddings, loss and gradients.  Propagation is in fact
+bit-exact for rows below the long-row threshold (sequential FMA order).
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+CASES = ["tiny_lightgcn_d64_k3", "tiny_lightgcn_d128_k4", "tiny_lightgcn_brand_d64_k3",
+         "tiny_fusion_d64_k3"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _orc():
+    from oracle import lgcn_oracle
+    return lgcn_oracle
+
+
+def _graph(g, dev, **kw):
+    from gcn_recommendation_b200.graph import NormAdjCSR
+    ib = (g["item_brand_item"], g["item_brand_brand"]) if "item_brand_item" in g else None
+    return NormAdjCSR.from_interactions(g["train_user"], g["train_item"], int(g["num_users"]),
+                                        int(g["num_items"]), int(g["num_brands"]), dev,
+                                        item_brand=ib, **kw)
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _t(a, dev, dt=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), device=dev).to(dt).contiguous()
+
+
+# ---------------------------------------------------------------------------- a1 graph
+@pytest.mark.parametrize("case", CASES)
+def test_csr_build_bit_exact(golden, dev, case):
+    g = golden(case)
+    csr = _graph(g, dev)
+    rows = np.repeat(np.arange(csr.n_rows), np.diff(csr.rowptr.cpu().numpy())).astype(np.int32)
+    assert np.array_equal(rows, g["adj_row"])
+    assert np.array_equal(csr.col.cpu().numpy(), g["adj_col"])
+    assert np.array_equal(_bits(csr.val.cpu().numpy()), _bits(g["adj_val"]))
+
+
+@pytest.mark.parametrize("case", CASES[:1] + CASES[2:3])
+def test_csr_from_reference_coo_tensor(golden, dev, case):
+    from gcn_recommendation_b200.graph import NormAdjCSR, csr_for
+    g = golden(case)
+    N = int(g["num_users"]) + int(g["num_items"]) + int(g["num_brands"])
+    idx = torch.from_numpy(np.vstack([g["adj_row"], g["adj_col"]]).astype(np.int64))
+    adj = torch.sparse_coo_tensor(idx, torch.from_numpy(g["adj_val"]), (N, N)).to(dev)  # main.py:336
+    csr = NormAdjCSR.from_sparse_coo(adj)
+    ref = _graph(g, dev)
+    assert torch.equal(csr.rowptr, ref.rowptr) and torch.equal(csr.col, ref.col)
+    assert torch.equal(csr.val, ref.val)
+    assert csr_for(adj) is csr_for(adj)
+    # an unsorted COO is coalesced first
+    perm = torch.randperm(idx.shape[1])
+    adj2 = torch.sparse_coo_tensor(idx[:, perm], torch.from_numpy(g["adj_val"])[perm], (N, N)).to(dev)
+    csr2 = NormAdjCSR.from_sparse_coo(adj2)
+    assert torch.equal(csr2.rowptr, ref.rowptr) and torch.equal(csr2.col, ref.col)
+    assert torch.equal(csr2.val, ref.val)
+
+
+# ---------------------------------------------------------------------------- a2 spmm
+@pytest.mark.parametrize("d", [16, 32, 64, 128, 256])
+def test_spmm_bit_exact_all_dims(dev, d):
+    from gcn_recommendation_b200 import ops, synth
+    from gcn_recommendation_b200.graph import NormAdjCSR
+    orc = _orc()
+    inter = synth.generate((500, 700, 2, 9000), seed=d)
+    tu, ti, _, _ = inter.split_validation()
+    csr = NormAdjCSR.from_interactions(tu, ti, 500, 700, 2, dev, long_row_threshold=0)
+    a = orc.build_norm_adj(tu, ti, 500, 700, 2)
+    rng = np.random.default_rng(d)
+    X = rng.standard_normal((1202, d), dtype=np.float32)
+    Y = ops.spmm(csr, _t(X, dev)).cpu().numpy()
+    ref = orc.spmm(a["rowptr"], a["col"], a["val"], X)
+    assert np.array_equal(_bits(Y), _bits(ref))
+    # empty rows (isolated brand nodes, cold items) produce exact zeros
+    deg = np.diff(a["rowptr"])
+    assert (deg == 0).any() and not Y[deg == 0].any()
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_spmm_long_row_plan_within_tolerance(dev, d):
+    """Rows longer than the threshold are summed segment-wise: deterministic, <= 1e-5."""
+    from gcn_recommendation_b200 import ops, synth
+    from gcn_recommendation_b200.graph import NormAdjCSR
+    orc = _orc()
+    inter = synth.generate("small", seed=3)
+    tu, ti, _, _ = inter.split_validation()
+    U, I, B = inter.num_users, inter.num_items, inter.num_brands
+    csr = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev, long_row_threshold=64, seg_len=32)
+    assert csr.n_long > 10 and csr.n_seg > csr.n_long
+    a = orc.build_norm_adj(tu, ti, U, I, B)
+    X = np.random.default_rng(0).standard_normal((U + I + B, d), dtype=np.float32)
+    xt = _t(X, dev)
+    Y1 = ops.spmm(csr, xt).cpu().numpy()
+    Y2 = ops.spmm(csr, xt).cpu().numpy()
+    assert np.array_equal(_bits(Y1), _bits(Y2)), "segment path must be deterministic"
+    ref = orc.spmm(a["rowptr"], a["col"], a["val"], X)
+    mx, fro = rel_err(Y1, ref)
+    assert mx < TOL and fro < TOL
+    short = np.diff(a["rowptr"]) <= 64
+    assert np.array_equal(_bits(Y1[short]), _bits(ref[short]))
+    # epilogues on the long-row path: add and mean
+    add = np.random.default_rng(1).standard_normal(X.shape, dtype=np.float32)
+    Ya = ops.spmm(csr, xt, addend=_t(add, dev)).cpu().numpy()
+    mx, fro = rel_err(Ya, add + ref)
+    assert mx < TOL and fro < TOL
+    Ym = ops.spmm(csr, xt, mean_layers=[_t(add, dev), xt]).cpu().numpy()
+    mx, fro = rel_err(Ym, ((add + X) + ref) / np.float32(3))
+    assert mx < TOL and fro < TOL
+
+
+@pytest.mark.parametrize("case", CASES[:3])
+def test_propagate_bit_exact_vs_reference(golden, dev, case):
+    from gcn_recommendation_b200 import ops
+    g = golden(case)
+    csr = _graph(g, dev)
+    E0 = np.concatenate([g["init/user_embedding.weight"], g["init/item_embedding.weight"],
+                         g["init/brand_embedding.weight"]], 0)
+    F = ops.propagate(csr, _t(E0, dev), int(g["K"])).cpu().numpy()
+    ref = np.concatenate([g["fwd/user"], g["fwd/item"], g["fwd/brand"]], 0)
+    assert np.array_equal(_bits(F), _bits(ref))
+
+
+# ---------------------------------------------------------------------------- drop-in models
+def _model(g, case, dev):
+    cfg = types.SimpleNamespace(embedding_dim=int(g["d"]), n_layers=int(g["K"]), debug=False)
+    U, I, B = int(g["num_users"]), int(g["num_items"]), int(g["num_brands"])
+    if "fusion" in case:
+        from models.lightgcn_fusion import LightGCN_Fusion
+        m = LightGCN_Fusion(U, I, B, cfg, pretrained_item_emb=g["init/item_content_embedding"])
+    else:
+        from models.lightgcn import LightGCN
+        m = LightGCN(U, I, B, cfg)
+    sd = {k[5:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("init/")}
+    m.load_state_dict(sd)
+    return m.to(dev)
+
+
+def _ref_coo(g, dev):
+    N = int(g["num_users"]) + int(g["num_items"]) + int(g["num_brands"])
+    idx = torch.from_numpy(np.vstack([g["adj_row"], g["adj_col"]]).astype(np.int64))
+    return torch.sparse_coo_tensor(idx, torch.from_numpy(g["adj_val"]), (N, N)).to(dev)
+
+
+def _bpr_loss_reg(fu, fp, fn, u0, p0, n0, lam):
+    """The loss the unmodified main.py applies to the drop-in's outputs (main.py:366-402)."""
+    ps = torch.sum(fu * fp, dim=1)
+    ns = torch.sum(fu * fn, dim=1)
+    bpr = -torch.mean(torch.log(torch.sigmoid(ps - ns) + 1e-8))
+    reg = lam * (u0.norm(2).pow(2) + p0.norm(2).pow(2) + n0.norm(2).pow(2)) / float(len(fu))
+    return bpr + reg
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_dropin_forward_backward_under_reference_loop(golden, dev, case):
+    """Drive the drop-in module the way main.train does (main.py:488-531): forward on the COO
+    tensor, main.py's own loss, autograd backward, torch Adam."""
+    g = golden(case)
+    model = _model(g, case, dev)
+    adj = _ref_coo(g, dev)
+    opt = torch.optim.Adam(model.parameters(), lr=float(g["lr"]))
+    losses = []
+    for s in range(len(g["losses"])):
+        users = _t(g["batch_users"][s], dev, torch.int64)
+        pos = _t(g["batch_pos"][s], dev, torch.int64)
+        neg = _t(g["batch_neg"][s], dev, torch.int64)
+        opt.zero_grad()
+        fu, fi, fb, u0, i0 = model(adj, use_brand=True)
+        if s == 0:
+            ref = np.concatenate([g["fwd/user"], g["fwd/item"], g["fwd/brand"]], 0)
+            got = torch.cat([fu, fi, fb]).detach().cpu().numpy()
+            if "fusion" in case:
+                mx, fro = rel_err(got, ref)
+                assert mx < TOL and fro < TOL
+            else:
+                assert np.array_equal(_bits(got), _bits(ref))
+        loss = _bpr_loss_reg(fu[users], fi[pos], fi[neg], u0[users], i0[pos], i0[neg], float(g["lam"]))
+        loss.backward()
+        if s == 0:
+            for k, p in model.named_parameters():
+                mx, fro = rel_err(p.grad.cpu().numpy(), g["grad1/" + k])
+                assert mx < TOL and fro < TOL, (k, mx, fro)
+        opt.step()
+        losses.append(loss.item())
+    assert np.allclose(losses, g["losses"], rtol=2e-5, atol=0)
+    sd = model.state_dict()
+    for k in sd:
+        if k == "item_content_embedding":
+            continue
+        mx, fro = rel_err(sd[k].cpu().numpy(), g["final/" + k])
+        assert mx < 1e-3 and fro < 1e-5, (k, mx, fro)
+    assert list(sd.keys()) == [k[5:] for k in g if k.startswith("init/")]
+
+
+# ---------------------------------------------------------------------------- native engine
+@pytest.mark.parametrize("use_graph", [False, True])
+@pytest.mark.parametrize("case", CASES)
+def test_engine_training_matches_reference(golden, dev, case, use_graph):
+    g = golden(case)
+    model = _model(g, case, dev)
+    csr = _graph(g, dev)
+    eng = model.engine(csr, lr=float(g["lr"]), weight_decay=float(g["lam"]), batch_size=int(g["bs"]))
+    losses = []
+    for s in range(len(g["losses"])):
+        # host (pinned) batches, as the reference's DataLoader delivers them (main.py:462-464,492)
+        u = torch.from_numpy(g["batch_users"][s]).pin_memory()
+        p = torch.from_numpy(g["batch_pos"][s]).pin_memory()
+        n = torch.from_numpy(g["batch_neg"][s]).pin_memory()
+        losses.append(float(eng.bpr_step(u, p, n, use_graph=use_graph).item()))
+        if s == 0:
+            sd = model.state_dict()
+            for k in sd:
+                if k == "item_content_embedding":
+                    continue
+                mx, fro = rel_err(sd[k].cpu().numpy(), g["step1/" + k])
+                assert mx < 1e-4 and fro < TOL, (k, mx, fro)
+    assert np.allclose(losses, g["losses"], rtol=2e-5, atol=0), (losses, g["losses"])
+    sd = model.state_dict()
+    for k in sd:
+        if k == "item_content_embedding":
+            continue
+        mx, fro = rel_err(sd[k].cpu().numpy(), g["final/" + k])
+        assert mx < 1e-3 and fro < 1e-5, (k, mx, fro)
+    # the scatter buffers are clean again after every step
+    assert not eng.G1.any() and not eng.G2.any()
+
+
+def test_bpr_fused_vs_oracle_with_duplicates(dev):
+    from gcn_recommendation_b200 import ops
+    orc = _orc()
+    rng = np.random.default_rng(5)
+    U, I, d, bs = 50, 80, 64, 512               # tiny id space -> many duplicate rows per batch
+    F = rng.standard_normal((U + I + 1, d), dtype=np.float32) * 0.3
+    P = rng.standard_normal((U + I + 1, d), dtype=np.float32) * 0.3
+    u = rng.integers(0, U, bs)
+    p = rng.integers(0, I, bs)
+    n = rng.integers(0, I, bs)
+    loss, gF, gU, gI = orc.bpr_loss(F, P[:U], P[U:U + I], u, p, n, U, 1e-4)
+    gFd = torch.zeros((U + I + 1, d), device=dev)
+    gPd = torch.zeros((U + I + 1, d), device=dev)
+    out = ops.bpr_fused(_t(F, dev), _t(P, dev), _t(u, dev, torch.int64), _t(p, dev, torch.int64),
+                        _t(n, dev, torch.int64), U, 1e-4, grad_scale=0.25, gF=gFd, gP=gPd)
+    assert abs(out.item() - loss) <= TOL * abs(loss)
+    mx, fro = rel_err(gFd.cpu().numpy(), 0.25 * gF)
+    assert mx < TOL and fro < TOL
+    ref_gp = np.zeros_like(P)
+    ref_gp[:U] = gU
+    ref_gp[U:U + I] = gI
+    mx, fro = rel_err(gPd.cpu().numpy(), ref_gp)
+    assert mx < TOL and fro < TOL
+    ops.zero_rows(gFd, gPd, _t(u, dev, torch.int64), _t(p, dev, torch.int64), _t(n, dev, torch.int64), U)
+    assert not gFd.any() and not gPd.any()
+
+
+def test_adam_vs_oracle(dev):
+    from gcn_recommendation_b200 import ops
+    orc = _orc()
+    rng = np.random.default_rng(9)
+    n = 4099                                     # exercises the non-multiple-of-4 tail
+    p = rng.standard_normal(n, dtype=np.float32)
+    m = np.zeros(n, np.float32)
+    v = np.zeros(n, np.float32)
+    pd, md, vd = _t(p, dev), _t(m, dev), _t(v, dev)
+    step = torch.zeros(1, dtype=torch.int64, device=dev)
+    sc = torch.zeros(2, device=dev)
+    for t in range(1, 6):
+        gr = rng.standard_normal(n, dtype=np.float32) * 1e-2
+        orc.adam_step(p, gr, m, v, t)
+        ops.adam_tick(step, sc, 1e-3)
+        ops.adam(pd, _t(gr, dev), md, vd, sc)
+    assert int(step.item()) == 5
+    for a, b in ((pd, p), (md, m), (vd, v)):
+        mx, fro = rel_err(a.cpu().numpy(), b)
+        assert mx < TOL and fro < 1e-6
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_fusion_projection_vs_oracle(dev, d):
+    from gcn_recommendation_b200 import ops
+    orc = _orc()
+    rng = np.random.default_rng(d)
+    n, c = 333, 768
+    E = rng.standard_normal((n, d), dtype=np.float32) * 0.1
+    C = rng.standard_normal((n, c), dtype=np.float32)
+    W = rng.standard_normal((d, d + c), dtype=np.float32) * 0.05
+    b = rng.standard_normal(d, dtype=np.float32) * 0.1
+    gH = rng.standard_normal((n, d), dtype=np.float32)
+    H, pre = orc.fusion_forward(E, C, W, b)
+    gE, gW, gb = orc.fusion_backward(E, C, W, pre, gH)
+    Hd = ops.fusion_proj_fwd(_t(E, dev), _t(C, dev), _t(W, dev), _t(b, dev))
+    mx, fro = rel_err(Hd.cpu().numpy(), H)
+    assert mx < TOL and fro < TOL
+    gEd, gWd, gbd = ops.fusion_proj_bwd(_t(E, dev), _t(C, dev), _t(W, dev), Hd, _t(gH, dev))
+    for a, r in ((gEd, gE), (gWd, gW), (gbd, gb)):
+        mx, fro = rel_err(a.cpu().numpy(), r)
+        assert mx < TOL and fro < TOL
+
+
+# ---------------------------------------------------------------------------- a7 eval
+@pytest.mark.parametrize("case", CASES)
+def test_topk_ids_and_metrics_vs_reference(golden, dev, case):
+    from gcn_recommendation_b200 import ops
+    from gcn_recommendation_b200.engine import build_mask_csr
+    orc = _orc()
+    g = golden(case)
+    users = g["eval/users"]
+    targets = dict(zip(g["val_user"].tolist(), g["val_item"].tolist()))
+    tg = np.asarray([targets[u] for u in users.tolist()], np.int64)
+    mr, mc = build_mask_csr(users, g["train_user"], g["train_item"], int(g["num_users"]), dev)
+    omr, omc = orc.mask_csr(users, g["train_user"], g["train_item"], int(g["num_users"]))
+    assert np.array_equal(mr.cpu().numpy(), omr) and np.array_equal(mc.cpu().numpy(), omc)
+    ids, sc = ops.score_topk(_t(g["eval/F_user"], dev), _t(g["eval/F_item"], dev),
+                             _t(users, dev, torch.int64), mr, mc, 20)
+    oids, osc = orc.score_topk(g["eval/F_user"], g["eval/F_item"], users, omr, omc, 20)
+    assert np.array_equal(ids.cpu().numpy(), oids), "top-k ids must be bit-exact vs the oracle"
+    assert np.array_equal(_bits(sc.cpu().numpy()), _bits(osc))
+    # against the reference's own torch.topk: identical except inside fp32 near-ties
+    ref_ids = g["eval/topk_ids"]
+    diff_rows = np.where((ids.cpu().numpy() != ref_ids).any(1))[0]
+    for r in diff_rows:
+        gap = np.abs(np.diff(g["eval/topk_scores"][r]))
+        assert gap.min() <= 4e-7 * np.abs(g["eval/topk_scores"][r]).max()
+    sums = ops.eval_metrics(ids, _t(tg, dev, torch.int64)).cpu().numpy()
+    assert sums[0] / len(users) == pytest.approx(float(g["eval/recall"]), abs=1e-12)
+    assert sums[1] / len(users) == pytest.approx(float(g["eval/ndcg"]), abs=1e-12)
+
+
+def test_topk_without_mask_and_ragged_user_tile(dev):
+    from gcn_recommendation_b200 import ops
+    orc = _orc()
+    rng = np.random.default_rng(11)
+    Fu = rng.standard_normal((97, 128), dtype=np.float32)
+    Fi = rng.standard_normal((1111, 128), dtype=np.float32)
+    Fi[500] = Fi[20]                             # exact tie: lower id must come first
+    users = rng.permutation(97)[:71]
+    ids, sc = ops.score_topk(_t(Fu, dev), _t(Fi, dev), _t(users, dev, torch.int64), None, None, 20)
+    oids, osc = orc.score_topk(Fu, Fi, users, None, None, 20)
+    assert np.array_equal(ids.cpu().numpy(), oids)
+    assert np.array_equal(_bits(sc.cpu().numpy()), _bits(osc))
+
+
+# ---------------------------------------------------------------------------- properties
+def test_gowalla_shape_properties(dev):
+    """Size-independent checks at the full Gowalla shape (configs[1]): the normalised adjacency is
+    symmetric (<x, A y> == <A x, y>), propagation is linear, and a sampled set of rows matches
+    the oracle bit-exactly."""
+    from gcn_recommendation_b200 import ops, synth
+    from gcn_recommendation_b200.graph import NormAdjCSR
+    orc = _orc()
+    inter = synth.generate("gowalla", seed=0)
+    tu, ti, _, _ = inter.split_validation()
+    U, I, B = inter.num_users, inter.num_items, inter.num_brands
+    csr = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev)
+    N, d = U + I + B, 64
+    gen = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn((N, d), device=dev, generator=gen)
+    y = torch.randn((N, d), device=dev, generator=gen)
+    ax, ay = ops.spmm(csr, x), ops.spmm(csr, y)
+    lhs = (x.double() * ay.double()).sum().item()
+    rhs = (ax.double() * y.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), 1.0)
+    f1 = ops.propagate(csr, x, 3)
+    f2 = ops.propagate(csr, y, 3)
+    f12 = ops.propagate(csr, (x + 2 * y).contiguous(), 3)
+    mx, fro = rel_err((f1 + 2 * f2).cpu().numpy(), f12.cpu().numpy())
+    assert fro < TOL
+    a = orc.build_norm_adj(tu, ti, U, I, B)
+    assert np.array_equal(csr.col.cpu().numpy(), a["col"])
+    assert np.array_equal(_bits(csr.val.cpu().numpy()), _bits(a["val"]))
+    ref = orc.spmm(a["rowptr"], a["col"], a["val"], x.cpu().numpy())
+    got = ax.cpu().numpy()
+    short = np.diff(a["rowptr"]) <= csr.long_row_threshold
+    assert np.array_equal(_bits(got[short]), _bits(ref[short]))
+    mx, fro = rel_err(got, ref)
+    assert mx < TOL and fro < TOL
+
+
+def test_no_cpu_fallback(dev):
+    from gcn_recommendation_b200 import _lib, ops
+    with pytest.raises(_lib.LgcnError):
+        ops.adam(torch.zeros(8), torch.zeros(8), torch.zeros(8), torch.zeros(8), torch.zeros(2))

@@ -1,0 +1,139 @@
+"""CPU-side tests (-m "not gpu"): host logic, the synthetic generator and the C-ABI surface.
+No kernel is launched here."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol():
+    """liblgcn_b200.so loads and exports exactly what include/lgcn.h declares."""
+    from gcn_recommendation_b200 import _lib, build
+    lib_path = build.build()
+    hdr = open(os.path.join(ROOT, "include", "lgcn.h")).read()
+    declared = sorted(set(re.findall(r"LGCN_API[^;(]*?\b(lgcn_\w+)\s*\(", hdr)))
+    assert len(declared) >= 15
+    out = subprocess.check_output(["nm", "-D", "--defined-only", lib_path], text=True)
+    exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l and "lgcn_" in l)
+    assert exported == declared
+    assert _lib.exported_symbols() == declared
+    lib = _lib.load()
+    assert lib.lgcn_abi_version() == _lib.ABI_VERSION
+    assert lib.lgcn_sizeof_spmm_args() == ctypes.sizeof(_lib.SpmmArgs)
+    assert b"embedding dim" in lib.lgcn_error_string(-1)
+
+
+def test_argument_errors_are_reported_not_thrown():
+    from gcn_recommendation_b200 import _lib
+    lib = _lib.load()
+    a = _lib.SpmmArgs()
+    a.d = 48
+    assert lib.lgcn_spmm(ctypes.byref(a), None) == -1            # LGCN_E_BAD_DIM
+    a.d = 64
+    assert lib.lgcn_spmm(ctypes.byref(a), None) == -2            # null pointers
+    assert lib.lgcn_adam(None, None, None, None, None, 4, None, 0.9, 0.999, 1e-8, None) == -2
+    assert lib.lgcn_score_topk(None, None, None, 1, 1, 64, None, None, 64, None, None, None, 0, None) == -2
+
+
+def test_no_cpu_fallback_on_cpu_tensors():
+    from gcn_recommendation_b200 import _lib, ops
+    with pytest.raises(_lib.LgcnError):
+        ops.fusion_proj_fwd(torch.zeros(4, 64), torch.zeros(4, 768), torch.zeros(64, 832), torch.zeros(64))
+    with pytest.raises(_lib.LgcnError):
+        ops.score_topk(torch.zeros(4, 64), torch.zeros(9, 64), torch.arange(4))
+
+
+def test_product_never_imports_the_oracle():
+    """The product path must not route through oracle/ (or the reference)."""
+    for base in ("gcn_recommendation_b200", "models"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                    assert "liblgcn_oracle" not in src and "/root/reference" not in src, f
+
+
+@pytest.mark.parametrize("shape", ["tiny", "small"])
+def test_synthetic_generator_contract(shape):
+    from gcn_recommendation_b200 import synth
+    U, I, B, total, _, _ = synth.SHAPES[shape]
+    a = synth.generate(shape, seed=3)
+    b = synth.generate(shape, seed=3)
+    assert np.array_equal(a.train_user, b.train_user) and np.array_equal(a.train_item, b.train_item)
+    assert len(a.train_user) + len(a.test_user) == total
+    key = np.concatenate([a.train_user, a.test_user]) * I + np.concatenate([a.train_item, a.test_item])
+    assert len(np.unique(key)) == total, "pairs must be unique"
+    assert len(a.test_user) == U and len(np.unique(a.test_user)) == U
+    tu, ti, vu, vi = a.split_validation()
+    assert len(vu) == U and len(np.unique(vu)) == U
+    assert np.bincount(tu, minlength=U).min() >= 1     # >= 3 interactions per user
+    assert ti.max() < I and tu.max() < U
+
+
+def test_reference_on_disk_format(tmp_path):
+    import json
+    import pandas as pd
+    from gcn_recommendation_b200 import synth
+    inter = synth.generate("tiny", seed=0)
+    synth.write_reference_format(inter, str(tmp_path), synth.side_embeddings(inter.num_items, 8))
+    tr = pd.read_parquet(tmp_path / "train.parquet")
+    assert list(tr.columns) == ["user_idx", "item_idx"] and tr["user_idx"].dtype == np.int64
+    assert list(pd.read_parquet(tmp_path / "item_brand.parquet").columns) == ["item_idx", "brand_idx"]
+    st = json.load(open(tmp_path / "stats.json"))
+    assert st == {"num_users": 120, "num_items": 200, "num_brands": 1}
+    assert np.load(tmp_path / "item_embeddings.npy").shape == (200, 8)
+
+
+def test_long_row_plan_host_logic():
+    from gcn_recommendation_b200.graph import NormAdjCSR
+    deg = np.array([0, 3, 70, 1, 64, 65, 200, 0], np.int64)
+    rowptr = np.zeros(len(deg) + 1, np.int32)
+    rowptr[1:] = np.cumsum(deg)
+    nnz = int(rowptr[-1])
+    g = NormAdjCSR(torch.from_numpy(rowptr), torch.zeros(nnz, dtype=torch.int32),
+                   torch.zeros(nnz), n_cols=8, long_row_threshold=64, seg_len=32)
+    assert g.n_long == 3 and g.long_row_ids.tolist() == [2, 5, 6]
+    assert g.long_seg_ptr.tolist() == [0, 3, 6, 13] and g.n_seg == 13
+    g0 = NormAdjCSR(torch.from_numpy(rowptr), torch.zeros(nnz, dtype=torch.int32),
+                    torch.zeros(nnz), n_cols=8, long_row_threshold=0)
+    assert g0.n_long == 0 and g0.long_row_threshold == 0
+
+
+def test_mask_csr_matches_groupby_lists():
+    from gcn_recommendation_b200.engine import build_mask_csr
+    tu = np.array([3, 1, 3, 0, 1, 3], np.int64)
+    ti = np.array([9, 4, 2, 7, 1, 5], np.int64)
+    rp, col = build_mask_csr(np.array([3, 2, 1], np.int64), tu, ti, 4)
+    assert rp.tolist() == [0, 3, 3, 5] and col.tolist() == [2, 5, 9, 1, 4]
+
+
+def test_parameter_packing_keeps_identity_and_state_dict_keys():
+    import types
+    from models._packing import is_packed
+    from models.lightgcn import LightGCN
+    cfg = types.SimpleNamespace(embedding_dim=64, n_layers=3, debug=False)
+    m = LightGCN(10, 20, 1, cfg)
+    params = list(m.parameters())
+    opt = torch.optim.Adam(params, lr=1e-3)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    block = m.table_block()
+    assert is_packed(m._tables()) and block.shape == (31, 64)
+    assert all(a is b for a, b in zip(params, m.parameters()))
+    assert list(m.state_dict().keys()) == ["user_embedding.weight", "brand_embedding.weight",
+                                           "item_embedding.weight"]
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k])
+    assert torch.equal(block[:10], m.user_embedding.weight) and torch.equal(block[30:], m.brand_embedding.weight)
+    with pytest.raises(ValueError):
+        LightGCN(10, 20, 1, cfg, pretrained_item_emb=np.zeros((20, 32), np.float32))
+    from models.lightgcn_fusion import LightGCN_Fusion
+    with pytest.raises(ValueError):
+        LightGCN_Fusion(10, 20, 1, cfg)
+    del opt
