@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- LightGCN training step / epoch and full-rank eval on B200 (BASELINE.json metric:
+"LightGCN epoch s & SpMM HBM GB/s (frac of peak); eval users/s at 1/2/4/8 B200").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload amazon|gowalla|amazon_16th|amazon_64th|small]
+
+One "step" = one pass of the hot path over one batch: the reference's per-batch work
+(main.py:488-531: full K-layer propagation, BPR+L2, backward, dense Adam) on a 2048-triplet
+synthetic batch.  ``value`` = seconds per epoch = ms_per_step x steps_per_epoch (every step does
+identical work, so this is exact arithmetic, not a model).  Prints ONE JSON line (rank 0).
+
+Default workload: the Amazon-Books-2023-shape graph (BASELINE.json north_star target and
+configs[2]); it fits one B200 (about 70 GB) and its 7.5 GB tables are far larger than L2, which
+is what makes the HBM roofline meaningful.  ``--workload gowalla`` is configs[1].
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BS = 2048                     # reference main.py:86
+CPU_SAMPLE = {"amazon": ("amazon_64th", 64.0), "amazon_16th": ("amazon_64th", 4.0),
+              "amazon_64th": ("amazon_64th", 1.0), "gowalla": ("gowalla", 1.0),
+              "small": ("small", 1.0), "tiny": ("tiny", 1.0)}
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _spmm_bytes(N, nnz, d, extra_streams=0):
+    """Algorithmic bytes of one SpMM launch: col + rowptr + dinv-equivalent +
+    read X once + write Y (+ 4Nd per extra fused stream)."""
+    return 4 * nnz + 4 * (N + 1) + 4 * N + 4 * N * d * (2 + extra_streams)
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, uuid):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", uuid, f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def make_batches(tu, ti, num_items, n, seed, device=None, pin=False):
+    """n synthetic (user, pos, neg) int64 batches: uniformly sampled train rows, uniform random
+    negatives (the reference's rejection against positives, main.py:359-362, changes < 1e-5 of
+    the draws at these densities and nothing about the cost)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    E = len(tu)
+    for _ in range(n):
+        idx = torch.randint(0, E, (BS,), generator=g)
+        u, p = tu[idx], ti[idx]
+        ng = torch.randint(0, num_items, (BS,), generator=g)
+        if pin:
+            u, p, ng = u.pin_memory(), p.pin_memory(), ng.pin_memory()
+        if device is not None:
+            u, p, ng = u.to(device), p.to(device), ng.to(device)
+        out.append((u, p, ng))
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's torch port on the host cores
+# ----------------------------------------------------------------------------------------
+def cpu_reference(workload, steps, warmup, budget_s=150.0):
+    import torch
+    from gcn_recommendation_b200 import synth
+    from oracle.torch_port import TorchPort
+    sample, scale = CPU_SAMPLE[workload]
+    U, I, B, total, d, K = synth.SHAPES[sample]
+    inter = synth.generate(sample, seed=0)
+    tu, ti, _, _ = inter.split_validation()
+    port = TorchPort(tu, ti, U, I, B, d, K)
+    batches = make_batches(torch.from_numpy(tu), torch.from_numpy(ti), I, steps + warmup, 1)
+    t_all = time.perf_counter()
+    times = []
+    for s, (u, p, n) in enumerate(batches):
+        t0 = time.perf_counter()
+        port.step(u, p, n)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+        if time.perf_counter() - t_all > budget_s and len(times) >= 1:
+            break
+    step_s = float(np.mean(times))
+    full = synth.SHAPES[workload]
+    steps_per_epoch = -(-(full[3] - 2 * full[0]) // BS)
+    return dict(step_s=step_s, steps_timed=len(times), scale=scale, sample=sample,
+                epoch_s=step_s * scale * steps_per_epoch, steps_per_epoch=steps_per_epoch,
+                cores=torch.get_num_threads(), host_cpus=os.cpu_count(), d=d, K=K,
+                sample_desc=(f"{len(times)} full train steps (fwd {K}x torch.sparse.mm + BPR + backward "
+                             f"+ Adam, bs {BS}) of the oracle's torch port on the '{sample}' graph "
+                             f"(N={U + I + B}), time x{scale:g} (nnz ratio) x {steps_per_epoch} steps/epoch"))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference(args.workload, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "lightgcn_epoch_s", "value": r["epoch_s"], "unit": "s",
+        "n_gpus": args.gpus, "steps": r["steps_timed"], "warmup": args.warmup,
+        "ms_per_step": r["step_s"] * r["scale"] * 1e3, "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "batch": BS, "d": r["d"], "layers": r["K"],
+                   "steps_per_epoch": r["steps_per_epoch"], "cpu_sample": r["sample"]},
+        "cpu_baseline": {"value": r["epoch_s"], "unit": "s", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample_desc"]},
+        "e2e": {"value": r["epoch_s"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from gcn_recommendation_b200 import ops, synth
+    from gcn_recommendation_b200.engine import LightGCNEngine, build_mask_csr, xavier_uniform_table
+    from gcn_recommendation_b200.graph import NormAdjCSR
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+
+    U, I, B, total, d, K = synth.SHAPES[args.workload]
+    N = U + I + B
+    t0 = time.perf_counter()
+    inter = synth.generate_device(args.workload, dev, seed=0)
+    tu, ti, vu, vi = synth.split_validation_device(inter)
+    csr = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev)
+    del inter
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+    steps_per_epoch = -(-int(tu.numel()) // BS)
+    gen = torch.Generator(device=dev).manual_seed(42)
+    table = xavier_uniform_table([U, I, B], d, dev, gen)
+
+    if world > 1:
+        from gcn_recommendation_b200.dist import ShardedLightGCNEngine
+        eng = ShardedLightGCNEngine(csr, U, I, B, K, table, batch_size=BS)
+    else:
+        eng = LightGCNEngine(csr, U, I, B, K, table, batch_size=BS)
+
+    tu_h, ti_h = tu.cpu(), ti.cpu()
+    nb = args.steps + args.warmup
+    dev_batches = make_batches(tu_h, ti_h, I, nb, 1, device=dev)
+    host_batches = make_batches(tu_h, ti_h, I, nb, 2, pin=True)
+    use_graph = N < 1_000_000          # launch-bound shapes run the captured step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    # ---- value: inputs resident in HBM --------------------------------------------------
+    for s in range(args.warmup):
+        eng.bpr_step(*dev_batches[s], use_graph=use_graph)
+    barrier()
+    sampler = ClockSampler("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
+    ops.PROFILE = [] if not use_graph else None
+    l0 = ops.COUNTERS["launches"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for s in range(args.warmup, nb):
+        eng.bpr_step(*dev_batches[s], use_graph=use_graph)
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop() if sampler else None
+    launches = (ops.COUNTERS["launches"] - l0) if not use_graph else eng.launches_per_step * args.steps
+    prof, ops.PROFILE = ops.PROFILE, None
+    ms_per_step = ms_total / args.steps
+    last_loss = float(eng.loss.item())
+
+    # ---- kernel profile (CUDA events on the launching stream) ----------------------------
+    if prof is None:                    # graph-replayed shapes: a separate eager pass for the events
+        ops.PROFILE = prof = []
+        for s in range(args.warmup, nb):
+            eng.bpr_step(*dev_batches[s], use_graph=False)
+        torch.cuda.synchronize()
+        ops.PROFILE = None
+    torch.cuda.synchronize()
+    per_tag = {}
+    for tag, a, b in prof:
+        per_tag.setdefault(tag, []).append(a.elapsed_time(b))
+    g_local = eng.g
+    extra = {"plain": 0, "add": 1, "mean": K, "adam": 7}
+    kernels = {}
+    for tag, v in per_tag.items():
+        ms = float(np.mean(v))
+        by = _spmm_bytes(g_local.n_rows if world > 1 else N, g_local.nnz, d, extra[tag])
+        kernels[tag] = {"launches": len(v), "avg_ms": ms, "algorithmic_gb": by / 1e9,
+                        "achieved_gbs": by / 1e9 / (ms / 1e3)}
+    peak, peak_src = _peaks()
+    dom = "plain" if "plain" in kernels else sorted(kernels)[0]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "spmm_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(f"{args.workload}:{dom}")
+    roofline = {"bound": "hbm", "kernel": f"spmm_rows_kernel<{d},{dom}>",
+                "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_gb"] * 1e9,
+                "spmm_share_of_step": float(sum(np.sum(v) for v in per_tag.values()) / max(ms_total, 1e-9))
+                if not use_graph else None}
+
+    # ---- e2e: host batches through the public API, loss read back every step -------------
+    barrier()
+    ev0.record()
+    for s in range(args.warmup, nb):
+        loss = eng.bpr_step(*host_batches[s], use_graph=use_graph)
+        _ = loss.item()                                  # reference main.py:528 syncs each step
+    ev1.record()
+    barrier()
+    e2e_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+
+    # ---- full-rank eval on a sample of users ----------------------------------------------
+    ev = None
+    if world == 1 and args.eval_users > 0:
+        nu = min(args.eval_users, U)
+        eu = vu[:nu].contiguous()
+        tg = vi[:nu].contiguous()
+        mr, mc = build_mask_csr(eu.cpu().numpy(), tu_h.numpy(), ti_h.numpy(), U, dev)
+        eng.evaluate(eu[:64], tg[:64], mr[:65].contiguous(), mc, 20)          # warm-up
+        torch.cuda.synchronize()
+        ev0.record()
+        rec, ndcg, _ = eng.evaluate(eu, tg, mr, mc, 20)
+        ev1.record()
+        torch.cuda.synchronize()
+        ems = ev0.elapsed_time(ev1)
+        ev = {"users_per_s": nu / (ems / 1e3), "users": nu, "items": I, "ms": ems,
+              "recall@20": rec, "ndcg@20": ndcg,
+              "note": "one propagation + exact fp32 score/mask/top-20 over the full catalogue"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference(args.workload, 3, 1, budget_s=40.0)
+        cpu = {"value": r["epoch_s"], "unit": "s", "cores": r["cores"], "kind": "port",
+               "sample": r["sample_desc"], "host_cpus": r["host_cpus"]}
+
+    if rank == 0:
+        line = {
+            "metric": "lightgcn_epoch_s", "value": ms_per_step * steps_per_epoch / 1e3, "unit": "s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "num_users": U, "num_items": I, "nodes": N,
+                       "nnz": csr.nnz, "d": d, "layers": K, "batch": BS,
+                       "steps_per_epoch": steps_per_epoch,
+                       "parallelism": "single" if world == 1 else f"row-sharded x{world}",
+                       "l2": "tables (%.2f GB each) are larger than L2; no flush" % (4 * N * d / 1e9)
+                       if 4 * N * d > 2 * 126e6 else "working set is L2-sized: launch/L2-bound shape",
+                       "cuda_graph": use_graph, "setup_s": setup_s},
+            "clocks": clocks,
+            "e2e": {"value": e2e_ms * steps_per_epoch / 1e3, "unit": "s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": 3 * BS * 8, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "kernels": kernels, "eval": ev, "cpu_baseline": cpu,
+            "loss": last_loss,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="amazon", choices=sorted(CPU_SAMPLE))
+    ap.add_argument("--eval-users", type=int, default=9472)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

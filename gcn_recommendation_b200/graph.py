@@ -81,6 +81,8 @@ class NormAdjCSR:
         ``fl32(fl32(d_r*m)*d_c)`` (``:330-331``) formed on the GPU by ``lgcn_edge_weights``."""
         U, I, B = int(num_users), int(num_items), int(num_brands)
         N = U + I + B
+        if isinstance(train_user, torch.Tensor) and train_user.is_cuda:
+            return cls._from_interactions_device(train_user, train_item, U, I, B, item_brand, **kw)
         u = np.ascontiguousarray(train_user, dtype=np.int64)
         it = np.ascontiguousarray(train_item, dtype=np.int64) + U
         if len(u) and (u.min() < 0 or u.max() >= U or it.min() < U or it.max() >= U + I):
@@ -126,6 +128,50 @@ class NormAdjCSR:
                                          _lib.ptr(t_dinv), _lib.ptr(t_mult, allow_none=True),
                                          _lib.ptr(t_val), N, _lib.stream_ptr(device)))
         g = cls(t_rowptr, t_col, t_val, N, rowptr_host=rp32, **kw)
+        g.dinv = t_dinv
+        return g
+
+    @classmethod
+    def _from_interactions_device(cls, train_user, train_item, U, I, B, item_brand=None, **kw):
+        """Same construction with the edge list already in HBM: the (row, col) sort / dedupe /
+        degree count run as torch device ops (integer work, bit-exact); ``d = np.power(deg,
+        -0.5)`` is still the host numpy call of reference ``main.py:328`` (O(N))."""
+        dev = train_user.device
+        N = U + I + B
+        u = train_user.to(torch.int64)
+        it = train_item.to(torch.int64) + U
+        parts = [u * N + it, it * N + u]
+        if item_brand is not None:
+            ib_i = torch.as_tensor(item_brand[0], device=dev).to(torch.int64) + U
+            ib_b = torch.as_tensor(item_brand[1], device=dev).to(torch.int64) + U + I
+            parts += [ib_i * N + ib_b, ib_b * N + ib_i]
+        key = torch.sort(torch.cat(parts)).values
+        del parts
+        ukey, mult = torch.unique_consecutive(key, return_counts=True)
+        del key
+        r = torch.div(ukey, N, rounding_mode="floor")
+        c = (ukey - r * N).to(torch.int32)
+        counts = torch.bincount(r, minlength=N)
+        rowptr = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=rowptr[1:])
+        if int(rowptr[-1].item()) >= 2 ** 31:
+            raise ValueError("nnz does not fit int32")
+        unit = bool(mult.numel() == 0 or int(mult.max().item()) == 1)
+        deg = counts if unit else torch.bincount(r, weights=mult.to(torch.float64), minlength=N)
+        del r, ukey
+        deg_h = deg.cpu().numpy().astype(np.float32)
+        with np.errstate(divide="ignore"):
+            dinv = np.power(deg_h, np.float32(-0.5)).astype(np.float32)   # main.py:328
+        dinv[np.isinf(dinv)] = 0.0                                         # main.py:329
+        t_rowptr = rowptr.to(torch.int32)
+        t_dinv = torch.from_numpy(dinv).to(dev)
+        t_mult = None if unit else mult.to(torch.float32)
+        t_val = torch.empty(c.numel(), dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        _lib.check(lib.lgcn_edge_weights(_lib.ptr(t_rowptr, "i32"), _lib.ptr(c, "i32"),
+                                         _lib.ptr(t_dinv), _lib.ptr(t_mult, allow_none=True),
+                                         _lib.ptr(t_val), N, _lib.stream_ptr(dev)))
+        g = cls(t_rowptr, c, t_val, N, **kw)
         g.dinv = t_dinv
         return g
 

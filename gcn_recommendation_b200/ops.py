@@ -13,6 +13,26 @@ from . import _lib
 from ._lib import SPMM_ADAM, SPMM_ADD, SPMM_MEAN, SPMM_PLAIN, SpmmArgs, check, ptr, stream_ptr
 
 
+# kernels of this library launched so far (bench.py's gpu_launches) and an optional per-launch
+# CUDA-event profile of the SpMM (bench.py's roofline): set PROFILE to a list to collect
+# (tag, start_event, end_event) on the launching stream.
+COUNTERS = {"launches": 0}
+PROFILE = None
+
+
+def _launch_spmm(a, g, dev, tag):
+    n_kernels = 3 if (a.long_row_threshold > 0 and a.n_long > 0) else 1
+    COUNTERS["launches"] += n_kernels
+    if PROFILE is None:
+        check(_lib.load().lgcn_spmm(ctypes.byref(a), stream_ptr(dev)))
+        return
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    check(_lib.load().lgcn_spmm(ctypes.byref(a), stream_ptr(dev)))
+    e.record()
+    PROFILE.append((tag, s, e))
+
+
 def _spmm_args(g, x, mode, d):
     a = SpmmArgs()
     a.rowptr, a.col, a.val = ptr(g.rowptr, "i32"), ptr(g.col, "i32"), ptr(g.val)
@@ -58,7 +78,7 @@ def spmm(g, x, out=None, addend=None, mean_layers=None):
     else:
         a = _spmm_args(g, x, SPMM_PLAIN, d)
     a.y = ptr(out)
-    check(_lib.load().lgcn_spmm(ctypes.byref(a), stream_ptr(x.device)))
+    _launch_spmm(a, g, x.device, ("plain", "add", "mean")[a.mode])
     return out
 
 
@@ -76,7 +96,7 @@ def spmm_adam(g, x, p, m, v, adam_scalars, addend=None, addend2=None, betas=(0.9
     a.adam_scalars = ptr(adam_scalars)
     a.beta1, a.beta2, a.eps = betas[0], betas[1], eps
     a.g_out = ptr(g_out, allow_none=True)
-    check(_lib.load().lgcn_spmm(ctypes.byref(a), stream_ptr(x.device)))
+    _launch_spmm(a, g, x.device, "adam")
 
 
 def propagate(g, e0, n_layers, out=None, work=None):
@@ -118,6 +138,7 @@ def bpr_fused(F, P, users, pos, neg, num_users, lam, grad_scale=1.0, gF=None, gP
         flags |= _lib.BPR_NO_GRAD
     if gp_includes_gf:
         flags |= _lib.BPR_GP_INCLUDES_GF
+    COUNTERS["launches"] += 2
     check(_lib.load().lgcn_bpr_fused(ptr(F), ptr(P), ptr(users, "i64"), ptr(pos, "i64"),
                                      ptr(neg, "i64"), bs, d, num_users, lam, grad_scale, flags,
                                      ptr(sample_ws), ptr(loss_out), ptr(gF, allow_none=True),
@@ -127,17 +148,20 @@ def bpr_fused(F, P, users, pos, neg, num_users, lam, grad_scale=1.0, gF=None, gP
 
 def zero_rows(t0, t1, users, pos, neg, num_users):
     d = t0.shape[1]
+    COUNTERS["launches"] += 1
     check(_lib.load().lgcn_zero_rows(ptr(t0), ptr(t1, allow_none=True), ptr(users, "i64"),
                                      ptr(pos, "i64"), ptr(neg, "i64"), users.numel(), d, num_users,
                                      stream_ptr(t0.device)))
 
 
 def adam_tick(step_dev, scalars, lr, betas=(0.9, 0.999)):
+    COUNTERS["launches"] += 1
     check(_lib.load().lgcn_adam_tick(ptr(step_dev, "i64"), ptr(scalars), lr, betas[0], betas[1],
                                      stream_ptr(scalars.device)))
 
 
 def adam(p, g0, m, v, scalars, g1=None, betas=(0.9, 0.999), eps=1e-8):
+    COUNTERS["launches"] += 1
     check(_lib.load().lgcn_adam(ptr(p), ptr(g0), ptr(g1, allow_none=True), ptr(m), ptr(v),
                                 p.numel(), ptr(scalars), betas[0], betas[1], eps,
                                 stream_ptr(p.device)))
@@ -152,6 +176,7 @@ def fusion_proj_fwd(e_id, content, W, b, out=None):
         raise _lib.LgcnError("fusion_proj: shape mismatch")
     if out is None:
         out = torch.empty((n, d), dtype=torch.float32, device=e_id.device)
+    COUNTERS["launches"] += 1
     check(_lib.load().lgcn_fusion_proj_fwd(ptr(e_id), ptr(content), ptr(W), ptr(b), n, d, c,
                                            ptr(out), stream_ptr(e_id.device)))
     return out
@@ -167,6 +192,7 @@ def fusion_proj_bwd(e_id, content, W, H, gH, g_eid=None, gW=None, gb=None):
         gW = torch.zeros((d, d + c), dtype=torch.float32, device=dev)
     if gb is None:
         gb = torch.zeros((d,), dtype=torch.float32, device=dev)
+    COUNTERS["launches"] += 2
     check(_lib.load().lgcn_fusion_proj_bwd(ptr(e_id), ptr(content), ptr(W), ptr(H), ptr(gH), n, d,
                                            c, ptr(g_eid), ptr(gW), ptr(gb), stream_ptr(dev)))
     return g_eid, gW, gb
@@ -183,6 +209,7 @@ def score_topk(F_user, F_item, users, mask_rowptr=None, mask_col=None, k=20):
     lib = _lib.load()
     wsb = lib.lgcn_score_topk_workspace(nu, F_item.shape[0], d, k)
     ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+    COUNTERS["launches"] += 1
     check(lib.lgcn_score_topk(ptr(F_user), ptr(F_item), ptr(users, "i64"), nu, F_item.shape[0], d,
                               ptr(mask_rowptr, "i64", allow_none=True),
                               ptr(mask_col, "i32", allow_none=True), k, ptr(ids, "i32"), ptr(sc),
@@ -195,6 +222,7 @@ def eval_metrics(topk_ids, targets, sums=None):
     nu, k = topk_ids.shape
     if sums is None:
         sums = torch.zeros(2, dtype=torch.float64, device=topk_ids.device)
+    COUNTERS["launches"] += 1
     check(_lib.load().lgcn_eval_metrics(ptr(topk_ids, "i32"), ptr(targets, "i64"), nu, k,
                                         ptr(sums, "f64"), stream_ptr(topk_ids.device)))
     return sums

@@ -154,3 +154,74 @@ def write_reference_format(inter: Interactions, out_dir, content: np.ndarray | N
                    "num_brands": inter.num_brands}, f)
     if content is not None:
         np.save(os.path.join(out_dir, "item_embeddings.npy"), content.astype(np.float32))
+
+
+SHAPES["amazon_64th"] = (160_937, 68_750, 1, 782_812, 128, 4)
+
+
+def generate_device(shape, device, seed=0, alpha=0.8, min_degree=3):
+    """Same generator as :func:`generate`, evaluated with torch on ``device`` (the 50 M-pair
+    Amazon shape takes ~2 minutes in numpy on 8 cores; on the GPU it is a second).  The random
+    streams differ from numpy's, the distributional shape is identical.  Returns an
+    :class:`Interactions` whose arrays are int64 torch tensors on ``device``."""
+    import torch
+
+    if isinstance(shape, str):
+        U, I, B, total, _, _ = SHAPES[shape]
+    else:
+        U, I, B, total = shape
+    gen = torch.Generator(device=device).manual_seed(seed)
+    extra = total - U * min_degree
+    if extra < 0:
+        raise ValueError("total interactions < num_users * min_degree")
+    w = torch.exp(torch.randn(U, device=device, generator=gen, dtype=torch.float64))
+    add = torch.floor(w / w.sum() * extra).to(torch.int64)
+    short = extra - int(add.sum().item())
+    if short > 0:
+        add[torch.randperm(U, device=device, generator=gen)[:short]] += 1
+    deg = add + min_degree
+    cdf = torch.cumsum(torch.arange(1, I + 1, device=device, dtype=torch.float64) ** (-alpha), 0)
+    cdf = cdf / cdf[-1]
+    rank_to_item = torch.randperm(I, device=device, generator=gen)
+
+    def draw(n):
+        r = torch.rand(n, device=device, generator=gen, dtype=torch.float64)
+        return rank_to_item[torch.searchsorted(cdf, r, right=True).clamp_(0, I - 1)]
+
+    users = torch.repeat_interleave(torch.arange(U, device=device), deg)
+    items = draw(users.numel())
+    for _ in range(200):
+        key = users * I + items
+        sk, order = torch.sort(key, stable=True)
+        dup_sorted = torch.zeros_like(sk, dtype=torch.bool)
+        dup_sorted[1:] = sk[1:] == sk[:-1]
+        dup = order[dup_sorted]
+        nd = dup.numel()
+        if nd == 0:
+            break
+        uni = torch.randint(0, I, (nd,), device=device, generator=gen)
+        coin = torch.rand(nd, device=device, generator=gen) < 0.5
+        items[dup] = torch.where(coin, draw(nd), uni)
+    else:  # pragma: no cover
+        raise RuntimeError("could not make interactions unique")
+    perm = torch.randperm(users.numel(), device=device, generator=gen)
+    users, items = users[perm], items[perm]
+    su, order = torch.sort(users, stable=True)
+    last = torch.ones_like(su, dtype=torch.bool)
+    last[:-1] = su[1:] != su[:-1]
+    is_test = torch.zeros_like(last)
+    is_test[order[last]] = True
+    return Interactions(U, I, B, users[~is_test], items[~is_test], users[is_test], items[is_test])
+
+
+def split_validation_device(inter):
+    """torch/device version of :meth:`Interactions.split_validation`."""
+    import torch
+
+    u = inter.train_user
+    su, order = torch.sort(u, stable=True)
+    first = torch.ones_like(su, dtype=torch.bool)
+    first[1:] = su[1:] != su[:-1]
+    is_val = torch.zeros_like(first)
+    is_val[order[first]] = True
+    return u[~is_val], inter.train_item[~is_val], u[is_val], inter.train_item[is_val]

@@ -174,3 +174,30 @@ def test_eval_topk_and_metrics(golden, case):
     rec, ndcg = orc.recall_ndcg(ids, targets)
     assert rec == pytest.approx(float(g["eval/recall"]), abs=1e-12)
     assert ndcg == pytest.approx(float(g["eval/ndcg"]), abs=1e-12)
+
+
+@pytest.mark.parametrize("case", CASES[:2])
+def test_torch_port_tracks_reference(golden, case):
+    """oracle/torch_port.py (the timed CPU baseline) reproduces the reference's loss curve,
+    final parameters and validation metrics on the golden run."""
+    import torch
+    from oracle.torch_port import TorchPort
+    g = golden(case)
+    torch.set_num_threads(1)
+    U, I, B = int(g["num_users"]), int(g["num_items"]), int(g["num_brands"])
+    port = TorchPort(g["train_user"], g["train_item"], U, I, B, int(g["d"]), int(g["K"]),
+                     lr=float(g["lr"]), lam=float(g["lam"]), seed=42)
+    assert np.array_equal(port.user.weight.detach().numpy(), g["init/user_embedding.weight"])
+    assert np.array_equal(port.item.weight.detach().numpy(), g["init/item_embedding.weight"])
+    losses = [port.step(g["batch_users"][s], g["batch_pos"][s], g["batch_neg"][s])
+              for s in range(len(g["losses"]))]
+    assert np.allclose(losses, g["losses"], rtol=1e-6, atol=0)
+    assert np.allclose(port.item.weight.detach().numpy(), g["final/item_embedding.weight"],
+                       rtol=0, atol=1e-7)
+    users, targets = orc.eval_pairs(g["val_user"], g["val_item"])
+    lists = {}
+    for u, i in zip(g["train_user"].tolist(), g["train_item"].tolist()):
+        lists.setdefault(u, []).append(i)
+    rec, ndcg = port.evaluate(users, targets, lists, 20)
+    assert rec == pytest.approx(float(g["eval/recall"]), abs=1e-12)
+    assert ndcg == pytest.approx(float(g["eval/ndcg"]), abs=1e-12)
