@@ -17,18 +17,17 @@ c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctyp
 
 SPMM_PLAIN, SPMM_ADD, SPMM_MEAN, SPMM_ADAM = 0, 1, 2, 3
 BPR_GP_INCLUDES_GF, BPR_NO_GRAD = 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class SpmmArgs(ctypes.Structure):
     """struct lgcn_spmm_args (include/lgcn.h)."""
     _fields_ = [
-        ("rowptr", c_vp), ("col", c_vp), ("val", c_vp), ("x", c_vp),
+        ("rowptr", c_vp), ("colval", c_vp), ("x", c_vp),
         ("n_rows", c_i64), ("d", c_i32), ("mode", c_i32),
         ("y", c_vp), ("addend", c_vp), ("layers", c_vp * 8), ("n_layers", c_i32),
-        ("long_row_threshold", c_i32), ("n_long", c_i32),
-        ("long_row_ids", c_vp), ("long_seg_ptr", c_vp), ("seg_len", c_i32), ("n_seg", c_i32),
-        ("seg_ws", c_vp),
+        ("n_long", c_i32), ("long_row_ids", c_vp), ("long_rowptr", c_vp), ("long_colval", c_vp),
+        ("long_seg_ptr", c_vp), ("seg_len", c_i32), ("n_seg", c_i32), ("seg_ws", c_vp),
         ("addend2", c_vp), ("p", c_vp), ("m", c_vp), ("v", c_vp), ("adam_scalars", c_vp),
         ("beta1", c_f32), ("beta2", c_f32), ("eps", c_f32), ("g_out", c_vp),
     ]

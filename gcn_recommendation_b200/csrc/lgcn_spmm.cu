@@ -3,74 +3,44 @@
 // Replaces torch.sparse.mm (reference models/lightgcn.py:45, models/lightgcn_fusion.py:56),
 // its autograd backward (A is symmetric, so the same kernel serves), the layer mean
 // (reference models/lightgcn.py:54) and, in ADAM mode, optimizer.step() (reference
-// main.py:526).
+// main.py:526).  HBM-bound gather/stream work: no tensor cores.
 //
-// Mapping: a table row of d floats is owned by a sub-warp group of d/4 lanes (float4 per
-// lane); every lane owns fixed feature columns, so one row is a SEQUENTIAL fp32 FMA chain
-// in ascending column order -- bit-equal to the CPU reference -- while the loads of the
-// gathered rows are issued UNROLL deep ahead of the FMAs.  HBM-bound: no tensor cores.
+// Mapping.  A table row of d floats is owned by a "worker" = sub-warp group of d/4 lanes
+// (float4 per lane; one warp at d=128, a half warp at d=64).  Every lane owns fixed feature
+// columns, so one output row is a SEQUENTIAL fp32 FMA chain in ascending column order --
+// bit-equal to the CPU reference.
+//
+// A worker owns a CHUNK of R consecutive rows, whose entries are one contiguous range of the
+// packed {col,val} array.  It walks that range as a flat stream: {col,val} tiles are loaded
+// coalesced one tile ahead, the gathers of X rows are issued UNROLL deep ahead of the FMAs and
+// do not drain at row boundaries (average degree is ~4, so per-row pipelines would be latency
+// bound), and the row an entry belongs to is found with one ballot over the per-lane row ends.
+// Finished rows are staged in shared memory; the epilogue then streams the chunk's R rows with
+// all of its operand loads independent (mean of the earlier layers / Horner addend / Adam).
+#include <limits.h>
+
 #include "lgcn_common.cuh"
 
 namespace lgcn {
 
-struct SpmmParams {
-    lgcn_spmm_args a;
+constexpr int kUnroll = 8;
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+
+template <int D>
+struct ChunkCfg {
+    using G = RowGeom<D>;
+    static constexpr int RMAX = (2048 / D) < 4 ? 4 : (2048 / D);
+    static constexpr int R = G::LANES < RMAX ? G::LANES : RMAX;      // rows per worker chunk
+    static constexpr int WORKERS = kWarps * G::GROUPS;                // workers per CTA
+    static constexpr int ROWS_PER_CTA = WORKERS * R;
+    static constexpr size_t SMEM = (size_t)ROWS_PER_CTA * D * sizeof(float);
 };
 
-constexpr int kUnroll = 8;
-constexpr int kThreads = 256;
-
-// Accumulate entries [beg, beg+deg) of one CSR row into acc for the calling group.
-// All 32 lanes of the warp must call this together (loop bounds are made warp-uniform).
-template <int D>
-__device__ __forceinline__ void accumulate_range(const int32_t *__restrict__ col,
-                                                 const float *__restrict__ val,
-                                                 const float *__restrict__ X, int beg, int deg,
-                                                 float4 (&acc)[RowGeom<D>::VEC]) {
-    using G = RowGeom<D>;
-    const int lane = threadIdx.x & 31;
-    const int sub = lane % G::LANES;
-    int maxdeg = deg;
-#pragma unroll
-    for (int off = G::LANES; off < 32; off <<= 1)
-        maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, off));
-
-    for (int base = 0; base < maxdeg; base += G::LANES) {
-        int c = 0;
-        float w = 0.0f;
-        if (base + sub < deg) {
-            c = ld_stream_i32(col + beg + base + sub);
-            w = ld_stream_f32(val + beg + base + sub);
-        }
-        const int cnt = min(G::LANES, deg - base);         // may be <= 0 for a finished group
-        const int maxcnt = min(G::LANES, maxdeg - base);   // warp-uniform
-        for (int j = 0; j < maxcnt; j += kUnroll) {
-            float4 x[kUnroll][G::VEC];
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const int cj = __shfl_sync(0xffffffffu, c, j + u, G::LANES);
-                if (j + u < cnt) {
-                    const float *src = X + (size_t)cj * D + sub * 4;
-#pragma unroll
-                    for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const float wj = __shfl_sync(0xffffffffu, w, j + u, G::LANES);
-                if (j + u < cnt) {
-#pragma unroll
-                    for (int v = 0; v < G::VEC; ++v) fma4(acc[v], wj, x[u][v]);
-                }
-            }
-        }
-    }
-}
-
-// Apply the epilogue for local row `row` (group-cooperative; each lane owns 4*VEC columns).
+// ---- epilogue for one row held in registers (long-row combine path) -----------------------
 template <int D, int MODE>
-__device__ __forceinline__ void epilogue(const lgcn_spmm_args &a, int64_t row,
-                                         float4 (&acc)[RowGeom<D>::VEC]) {
+__device__ __forceinline__ void epilogue_row(const lgcn_spmm_args &a, int64_t row,
+                                             float4 (&acc)[RowGeom<D>::VEC]) {
     using G = RowGeom<D>;
     const int sub = (threadIdx.x & 31) % G::LANES;
 #pragma unroll
@@ -83,7 +53,6 @@ __device__ __forceinline__ void epilogue(const lgcn_spmm_args &a, int64_t row,
             add4(g, acc[v]);
             st_f4(a.y + off, g);
         } else if (MODE == LGCN_SPMM_MEAN) {
-            // sequential sum E_0 + E_1 + ... + E_{n-1} + (A x), then a true division
             float4 s = ld_stream_f4(a.layers[0] + off);
             for (int l = 1; l < a.n_layers; ++l) {
                 const float4 t = ld_stream_f4(a.layers[l] + off);
@@ -91,88 +60,266 @@ __device__ __forceinline__ void epilogue(const lgcn_spmm_args &a, int64_t row,
             }
             add4(s, acc[v]);
             const float div = (float)(a.n_layers + 1);
-            s.x = __fdiv_rn(s.x, div);
-            s.y = __fdiv_rn(s.y, div);
-            s.z = __fdiv_rn(s.z, div);
-            s.w = __fdiv_rn(s.w, div);
+            s.x = __fdiv_rn(s.x, div); s.y = __fdiv_rn(s.y, div);
+            s.z = __fdiv_rn(s.z, div); s.w = __fdiv_rn(s.w, div);
             st_f4(a.y + off, s);
         } else {  // LGCN_SPMM_ADAM
             float4 g = acc[v];
-            if (a.addend) {
-                const float4 t = ld_stream_f4(a.addend + off);
-                add4(g, t);
-            }
-            if (a.addend2) {
-                const float4 t = ld_stream_f4(a.addend2 + off);
-                add4(g, t);
-            }
+            if (a.addend) { const float4 t = ld_stream_f4(a.addend + off); add4(g, t); }
+            if (a.addend2) { const float4 t = ld_stream_f4(a.addend2 + off); add4(g, t); }
             float4 p = *reinterpret_cast<const float4 *>(a.p + off);
             float4 m = *reinterpret_cast<const float4 *>(a.m + off);
             float4 vv = *reinterpret_cast<const float4 *>(a.v + off);
             const float ss = __ldg(a.adam_scalars), bs = __ldg(a.adam_scalars + 1);
             adam4(p, m, vv, g, ss, bs, a.beta1, a.beta2, a.eps);
-            st_f4(a.p + off, p);
-            st_f4(a.m + off, m);
-            st_f4(a.v + off, vv);
+            st_f4(a.p + off, p); st_f4(a.m + off, m); st_f4(a.v + off, vv);
             if (a.g_out) st_f4(a.g_out + off, g);
         }
     }
 }
 
-// ---- main kernel: one group per row ----------------------------------------------------
+// ---- chunk epilogue: stream the staged rows, operand loads batched ahead of the math ------
 template <int D, int MODE>
-__global__ void __launch_bounds__(kThreads) spmm_rows_kernel(const SpmmParams p) {
+__device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const float *stage,
+                                               int64_t r0, int nvr, unsigned long_bits) {
     using G = RowGeom<D>;
-    const lgcn_spmm_args &a = p.a;
-    const int lane = threadIdx.x & 31;
-    const int grp = lane / G::LANES;
-    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const int64_t row = warp * G::GROUPS + grp;
-    int beg = 0, deg = 0;
-    bool owner = false;
-    if (row < a.n_rows) {
-        beg = __ldg(a.rowptr + row);
-        deg = __ldg(a.rowptr + row + 1) - beg;
-        owner = true;
-        if (a.long_row_threshold > 0 && deg > a.long_row_threshold) {
-            deg = 0;        // handled by the segment kernels
-            owner = false;
+    using C = ChunkCfg<D>;
+    const int sub = (threadIdx.x & 31) % G::LANES;
+    constexpr int B = (MODE == LGCN_SPMM_ADAM || MODE == LGCN_SPMM_MEAN) ? 2 : 4;  // rows per batch
+    static_assert(C::R % B == 0, "chunk rows must be a multiple of the epilogue batch");
+    const float div = (float)(a.n_layers + 1);
+    float ss = 0.f, bs = 1.f;
+    if (MODE == LGCN_SPMM_ADAM) { ss = __ldg(a.adam_scalars); bs = __ldg(a.adam_scalars + 1); }
+#pragma unroll
+    for (int v = 0; v < G::VEC; ++v) {
+        const int coff = sub * 4 + v * G::LANES * 4;
+        for (int rb = 0; rb < C::R; rb += B) {
+            bool on[B];
+            size_t off[B];
+#pragma unroll
+            for (int i = 0; i < B; ++i) {
+                const int rr = rb + i;
+                on[i] = rr < nvr && !((long_bits >> rr) & 1u);
+                off[i] = (size_t)(r0 + rr) * D + coff;
+            }
+            if (MODE == LGCN_SPMM_PLAIN) {
+#pragma unroll
+                for (int i = 0; i < B; ++i)
+                    if (on[i]) st_f4(a.y + off[i], *reinterpret_cast<const float4 *>(stage + (rb + i) * D + coff));
+            } else if (MODE == LGCN_SPMM_ADD) {
+                float4 t[B];
+#pragma unroll
+                for (int i = 0; i < B; ++i) if (on[i]) t[i] = ld_stream_f4(a.addend + off[i]);
+#pragma unroll
+                for (int i = 0; i < B; ++i)
+                    if (on[i]) {
+                        const float4 y = *reinterpret_cast<const float4 *>(stage + (rb + i) * D + coff);
+                        add4(t[i], y);
+                        st_f4(a.y + off[i], t[i]);
+                    }
+            } else if (MODE == LGCN_SPMM_MEAN) {
+                float4 t[B][8];
+#pragma unroll
+                for (int i = 0; i < B; ++i)
+#pragma unroll
+                    for (int l = 0; l < 8; ++l)
+                        if (on[i] && l < a.n_layers) t[i][l] = ld_stream_f4(a.layers[l] + off[i]);
+#pragma unroll
+                for (int i = 0; i < B; ++i)
+                    if (on[i]) {
+                        float4 s = t[i][0];
+#pragma unroll
+                        for (int l = 1; l < 8; ++l) if (l < a.n_layers) add4(s, t[i][l]);
+                        const float4 y = *reinterpret_cast<const float4 *>(stage + (rb + i) * D + coff);
+                        add4(s, y);
+                        s.x = __fdiv_rn(s.x, div); s.y = __fdiv_rn(s.y, div);
+                        s.z = __fdiv_rn(s.z, div); s.w = __fdiv_rn(s.w, div);
+                        st_f4(a.y + off[i], s);
+                    }
+            } else {  // ADAM
+                float4 g[B], p[B], m[B], vv[B], g2[B];
+#pragma unroll
+                for (int i = 0; i < B; ++i)
+                    if (on[i]) {
+                        if (a.addend) g[i] = ld_stream_f4(a.addend + off[i]);
+                        if (a.addend2) g2[i] = ld_stream_f4(a.addend2 + off[i]);
+                        p[i] = ld_stream_f4(a.p + off[i]);
+                        m[i] = ld_stream_f4(a.m + off[i]);
+                        vv[i] = ld_stream_f4(a.v + off[i]);
+                    }
+#pragma unroll
+                for (int i = 0; i < B; ++i)
+                    if (on[i]) {
+                        float4 gr = *reinterpret_cast<const float4 *>(stage + (rb + i) * D + coff);
+                        if (a.addend) add4(gr, g[i]);
+                        if (a.addend2) add4(gr, g2[i]);
+                        adam4(p[i], m[i], vv[i], gr, ss, bs, a.beta1, a.beta2, a.eps);
+                        st_f4(a.p + off[i], p[i]); st_f4(a.m + off[i], m[i]); st_f4(a.v + off[i], vv[i]);
+                        if (a.g_out) st_f4(a.g_out + off[i], gr);
+                    }
+            }
         }
     }
+}
+
+// ---- main kernel: one worker per chunk of R rows ---------------------------------------------
+template <int D, int MODE>
+__global__ void __launch_bounds__(kThreads) spmm_chunk_kernel(const lgcn_spmm_args a) {
+    using G = RowGeom<D>;
+    using C = ChunkCfg<D>;
+    extern __shared__ __align__(16) float stage_all[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int grp = lane / G::LANES;
+    const int sub = lane % G::LANES;
+    const int gshift = grp * G::LANES;
+    const unsigned gbits = (G::LANES == 32) ? 0xffffffffu : ((1u << G::LANES) - 1u);
+    float *stage = stage_all + (size_t)((warp * G::GROUPS + grp) * C::R) * D;
+
+    const int64_t worker = ((int64_t)blockIdx.x * kWarps + warp) * G::GROUPS + grp;
+    const int64_t r0 = worker * C::R;
+    const int64_t left = a.n_rows - r0;
+    const int nvr = left <= 0 ? 0 : (left < C::R ? (int)left : C::R);
+
+    unsigned rb = 0, re = 0;
+    if (sub < nvr) {
+        rb = __ldg(a.rowptr + r0 + sub);
+        re = __ldg(a.rowptr + r0 + sub + 1);
+    }
+    const bool my_long = (rb >> 31) != 0;
+    const int my_beg = (int)(rb & 0x7fffffffu);
+    int my_end = (int)(re & 0x7fffffffu);
+    int chunk_beg = __shfl_sync(0xffffffffu, my_beg, 0, G::LANES);
+    int chunk_end = __shfl_sync(0xffffffffu, my_end, nvr > 0 ? nvr - 1 : 0, G::LANES);
+    if (nvr == 0) chunk_beg = chunk_end = 0;
+    if (sub >= nvr) my_end = INT_MAX;                    // sentinel: never passed
+    const unsigned long_bits = (__ballot_sync(0xffffffffu, my_long) >> gshift) & gbits;
+
+    const int n_e = chunk_end - chunk_beg;
+    int max_n = n_e;
+#pragma unroll
+    for (int off = G::LANES; off < 32; off <<= 1)
+        max_n = max(max_n, __shfl_xor_sync(0xffffffffu, max_n, off));
+
+    const int2 *cvp = reinterpret_cast<const int2 *>(a.colval) + chunk_beg;
+    int2 cv = make_int2(0, 0);
+    if (sub < n_e) cv = __ldg(cvp + sub);
+
     float4 acc[G::VEC];
 #pragma unroll
     for (int v = 0; v < G::VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    accumulate_range<D>(a.col, a.val, a.x, beg, deg, acc);
-    if (owner) epilogue<D, MODE>(a, row, acc);
+    int cur = 0;                                          // row (within the chunk) being summed
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int t = 0; t < max_n; t += G::LANES) {
+        int2 cvn = make_int2(0, 0);
+        if (t + G::LANES + sub < n_e) cvn = __ldg(cvp + t + G::LANES + sub);   // next tile, one ahead
+        const int cnt = min(n_e - t, G::LANES);           // entries of this tile (may be <= 0)
+        const int maxcnt = min(G::LANES, max_n - t);      // warp-uniform
+        for (int j = 0; j < maxcnt; j += kUnroll) {
+            float4 x[kUnroll][G::VEC];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int cj = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
+                if (j + u < cnt) {
+                    const float *src = a.x + (size_t)cj * D + sub * 4;
+#pragma unroll
+                    for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const float wj = __int_as_float(__shfl_sync(0xffffffffu, cv.y, j + u, G::LANES));
+                const int e = chunk_beg + t + j + u;
+                // rows of this chunk that end at or before e (one ballot, no per-row pointer chase)
+                const unsigned passed = (__ballot_sync(0xffffffffu, my_end <= e) >> gshift) & gbits;
+                if (j + u < cnt) {
+                    const int row = __popc(passed);
+                    if (row != cur) {                     // flush the finished row, zero the empty ones
+#pragma unroll
+                        for (int v = 0; v < G::VEC; ++v) {
+                            st_f4(stage + cur * D + sub * 4 + v * G::LANES * 4, acc[v]);
+                            acc[v] = zero4;
+                        }
+                        for (int r = cur + 1; r < row; ++r)
+#pragma unroll
+                            for (int v = 0; v < G::VEC; ++v)
+                                st_f4(stage + r * D + sub * 4 + v * G::LANES * 4, zero4);
+                        cur = row;
+                    }
+#pragma unroll
+                    for (int v = 0; v < G::VEC; ++v) fma4(acc[v], wj, x[u][v]);
+                }
+            }
+        }
+        cv = cvn;
+    }
+    // rows cur .. nvr-1: the last summed row, then trailing empty rows
+    if (cur < nvr) {
+#pragma unroll
+        for (int v = 0; v < G::VEC; ++v) st_f4(stage + cur * D + sub * 4 + v * G::LANES * 4, acc[v]);
+        for (int r = cur + 1; r < nvr; ++r)
+#pragma unroll
+            for (int v = 0; v < G::VEC; ++v) st_f4(stage + r * D + sub * 4 + v * G::LANES * 4, zero4);
+    }
+    __syncwarp();
+    chunk_epilogue<D, MODE>(a, stage, r0, nvr, long_bits);
 }
 
-// ---- long rows: one group per segment, partial sums to seg_ws ---------------------------
+// ---- long rows: one worker per segment, partial sums to seg_ws -----------------------------
 template <int D>
-__global__ void __launch_bounds__(kThreads) spmm_long_seg_kernel(const SpmmParams p) {
+__global__ void __launch_bounds__(kThreads) spmm_long_seg_kernel(const lgcn_spmm_args a) {
     using G = RowGeom<D>;
-    const lgcn_spmm_args &a = p.a;
     const int lane = threadIdx.x & 31;
     const int grp = lane / G::LANES;
     const int sub = lane % G::LANES;
-    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t warp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
     const int64_t seg = warp * G::GROUPS + grp;
     int beg = 0, deg = 0;
     if (seg < a.n_seg) {
-        // long row that owns this segment: last i with long_seg_ptr[i] <= seg
-        int lo = 0, hi = a.n_long;
+        int lo = 0, hi = a.n_long;                        // last i with long_seg_ptr[i] <= seg
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
             if (__ldg(a.long_seg_ptr + mid) <= seg) lo = mid; else hi = mid;
         }
-        const int row = __ldg(a.long_row_ids + lo);
-        const int rbeg = __ldg(a.rowptr + row), rend = __ldg(a.rowptr + row + 1);
+        const int rbeg = __ldg(a.long_rowptr + lo), rend = __ldg(a.long_rowptr + lo + 1);
         beg = rbeg + (int)(seg - __ldg(a.long_seg_ptr + lo)) * a.seg_len;
         deg = min(a.seg_len, rend - beg);
     }
+    int maxdeg = deg;
+#pragma unroll
+    for (int off = G::LANES; off < 32; off <<= 1)
+        maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, off));
     float4 acc[G::VEC];
 #pragma unroll
     for (int v = 0; v < G::VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    accumulate_range<D>(a.col, a.val, a.x, beg, deg, acc);
+    const int2 *cvp = reinterpret_cast<const int2 *>(a.long_colval) + beg;
+    for (int base = 0; base < maxdeg; base += G::LANES) {
+        int2 cv = make_int2(0, 0);
+        if (base + sub < deg) cv = __ldg(cvp + base + sub);
+        const int cnt = min(deg - base, G::LANES);
+        const int maxcnt = min(G::LANES, maxdeg - base);
+        for (int j = 0; j < maxcnt; j += kUnroll) {
+            float4 x[kUnroll][G::VEC];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int cj = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
+                if (j + u < cnt) {
+                    const float *src = a.x + (size_t)cj * D + sub * 4;
+#pragma unroll
+                    for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const float wj = __int_as_float(__shfl_sync(0xffffffffu, cv.y, j + u, G::LANES));
+                if (j + u < cnt) {
+#pragma unroll
+                    for (int v = 0; v < G::VEC; ++v) fma4(acc[v], wj, x[u][v]);
+                }
+            }
+        }
+    }
     if (seg < a.n_seg) {
 #pragma unroll
         for (int v = 0; v < G::VEC; ++v)
@@ -180,15 +327,14 @@ __global__ void __launch_bounds__(kThreads) spmm_long_seg_kernel(const SpmmParam
     }
 }
 
-// ---- long rows: combine the segment partials in order, then the epilogue ----------------
+// ---- long rows: combine the segment partials in order, then the epilogue -------------------
 template <int D, int MODE>
-__global__ void __launch_bounds__(kThreads) spmm_long_combine_kernel(const SpmmParams p) {
+__global__ void __launch_bounds__(kThreads) spmm_long_combine_kernel(const lgcn_spmm_args a) {
     using G = RowGeom<D>;
-    const lgcn_spmm_args &a = p.a;
     const int lane = threadIdx.x & 31;
     const int grp = lane / G::LANES;
     const int sub = lane % G::LANES;
-    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t warp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
     const int64_t i = warp * G::GROUPS + grp;
     if (i >= a.n_long) return;
     const int s0 = __ldg(a.long_seg_ptr + i), s1 = __ldg(a.long_seg_ptr + i + 1);
@@ -205,40 +351,47 @@ __global__ void __launch_bounds__(kThreads) spmm_long_combine_kernel(const SpmmP
             add4(acc[v], t);
         }
     }
-    epilogue<D, MODE>(a, __ldg(a.long_row_ids + i), acc);
+    epilogue_row<D, MODE>(a, __ldg(a.long_row_ids + i), acc);
 }
 
 template <int D, int MODE>
-static int launch_mode(const SpmmParams &p, cudaStream_t st) {
+static int launch_mode(const lgcn_spmm_args &a, cudaStream_t st) {
     using G = RowGeom<D>;
-    constexpr int rows_per_block = (kThreads / 32) * G::GROUPS;
-    const lgcn_spmm_args &a = p.a;
-    if (a.long_row_threshold > 0 && a.n_long > 0) {
-        const unsigned gs = (unsigned)((a.n_seg + rows_per_block - 1) / rows_per_block);
-        spmm_long_seg_kernel<D><<<gs, kThreads, 0, st>>>(p);
+    using C = ChunkCfg<D>;
+    constexpr int groups_per_block = kWarps * G::GROUPS;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(spmm_chunk_kernel<D, MODE>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    if (a.n_long > 0) {
+        const unsigned gs = (unsigned)((a.n_seg + groups_per_block - 1) / groups_per_block);
+        spmm_long_seg_kernel<D><<<gs, kThreads, 0, st>>>(a);
         LGCN_LAUNCH_CHECK();
     }
     if (a.n_rows > 0) {
-        const int64_t gb = (a.n_rows + rows_per_block - 1) / rows_per_block;
+        const int64_t gb = (a.n_rows + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
         if (gb > 0x7fffffffLL) return LGCN_E_TOO_LARGE;
-        spmm_rows_kernel<D, MODE><<<(unsigned)gb, kThreads, 0, st>>>(p);
+        spmm_chunk_kernel<D, MODE><<<(unsigned)gb, kThreads, C::SMEM, st>>>(a);
         LGCN_LAUNCH_CHECK();
     }
-    if (a.long_row_threshold > 0 && a.n_long > 0) {
-        const unsigned gc = (unsigned)((a.n_long + rows_per_block - 1) / rows_per_block);
-        spmm_long_combine_kernel<D, MODE><<<gc, kThreads, 0, st>>>(p);
+    if (a.n_long > 0) {
+        const unsigned gc = (unsigned)((a.n_long + groups_per_block - 1) / groups_per_block);
+        spmm_long_combine_kernel<D, MODE><<<gc, kThreads, 0, st>>>(a);
         LGCN_LAUNCH_CHECK();
     }
     return 0;
 }
 
 template <int D>
-static int launch_dim(const SpmmParams &p, cudaStream_t st) {
-    switch (p.a.mode) {
-        case LGCN_SPMM_PLAIN: return launch_mode<D, LGCN_SPMM_PLAIN>(p, st);
-        case LGCN_SPMM_ADD:   return launch_mode<D, LGCN_SPMM_ADD>(p, st);
-        case LGCN_SPMM_MEAN:  return launch_mode<D, LGCN_SPMM_MEAN>(p, st);
-        case LGCN_SPMM_ADAM:  return launch_mode<D, LGCN_SPMM_ADAM>(p, st);
+static int launch_dim(const lgcn_spmm_args &a, cudaStream_t st) {
+    switch (a.mode) {
+        case LGCN_SPMM_PLAIN: return launch_mode<D, LGCN_SPMM_PLAIN>(a, st);
+        case LGCN_SPMM_ADD:   return launch_mode<D, LGCN_SPMM_ADD>(a, st);
+        case LGCN_SPMM_MEAN:  return launch_mode<D, LGCN_SPMM_MEAN>(a, st);
+        case LGCN_SPMM_ADAM:  return launch_mode<D, LGCN_SPMM_ADAM>(a, st);
         default: return LGCN_E_BAD_ARG;
     }
 }
@@ -252,7 +405,7 @@ extern "C" int lgcn_spmm(const lgcn_spmm_args *args, lgcn_stream_t stream) {
     if (!dim_supported(a.d)) return LGCN_E_BAD_DIM;
     if (a.n_rows < 0 || !a.rowptr || !a.x) return LGCN_E_BAD_ARG;
     if (a.n_rows > 0x7fffffffLL) return LGCN_E_TOO_LARGE;
-    if (a.n_rows > 0 && (!a.col || !a.val)) return LGCN_E_BAD_ARG;
+    if (a.n_rows > 0 && !a.colval) return LGCN_E_BAD_ARG;
     switch (a.mode) {
         case LGCN_SPMM_PLAIN: if (!a.y) return LGCN_E_BAD_ARG; break;
         case LGCN_SPMM_ADD:   if (!a.y || !a.addend) return LGCN_E_BAD_ARG; break;
@@ -265,19 +418,17 @@ extern "C" int lgcn_spmm(const lgcn_spmm_args *args, lgcn_stream_t stream) {
             break;
         default: return LGCN_E_BAD_ARG;
     }
-    SpmmParams p;
-    p.a = a;
-    if (a.long_row_threshold > 0 && a.n_long > 0) {
-        if (!a.long_row_ids || !a.long_seg_ptr || !a.seg_ws || a.seg_len <= 0 || a.n_seg <= 0)
-            return LGCN_E_BAD_ARG;
-    }
+    if (a.n_long < 0) return LGCN_E_BAD_ARG;
+    if (a.n_long > 0 && (!a.long_row_ids || !a.long_rowptr || !a.long_colval || !a.long_seg_ptr ||
+                         !a.seg_ws || a.seg_len <= 0 || a.n_seg <= 0))
+        return LGCN_E_BAD_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (a.d) {
-        case 16:  return launch_dim<16>(p, st);
-        case 32:  return launch_dim<32>(p, st);
-        case 64:  return launch_dim<64>(p, st);
-        case 128: return launch_dim<128>(p, st);
-        case 256: return launch_dim<256>(p, st);
+        case 16:  return launch_dim<16>(a, st);
+        case 32:  return launch_dim<32>(a, st);
+        case 64:  return launch_dim<64>(a, st);
+        case 128: return launch_dim<128>(a, st);
+        case 256: return launch_dim<256>(a, st);
     }
     return LGCN_E_BAD_DIM;
 }

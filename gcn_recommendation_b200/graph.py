@@ -15,8 +15,8 @@ import torch
 
 from . import _lib
 
-LONG_ROW_THRESHOLD = 1024
-SEG_LEN = 512
+LONG_ROW_THRESHOLD = 256
+SEG_LEN = 128
 
 
 class NormAdjCSR:
@@ -34,29 +34,50 @@ class NormAdjCSR:
         self._seg_ws = {}
         self._plan_long_rows(long_row_threshold, seg_len, rowptr_host)
 
-    # ---- long-row plan (host logic, once per graph) ------------------------------------
+    # ---- kernel layout (once per graph) ------------------------------------------------
     def _plan_long_rows(self, threshold, seg_len, rowptr_host=None):
+        """Build what ``lgcn_spmm`` reads (include/lgcn.h): short rows as packed {col,val} pairs
+        with a flagged rowptr, long rows (more than ``threshold`` entries) moved to their own
+        CSR and cut into ``seg_len`` segments.  Host logic decides, device ops move the data."""
         self.long_row_threshold = int(threshold)
         self.seg_len = int(seg_len)
         self.n_long = 0
         self.n_seg = 0
-        self.long_row_ids = None
-        self.long_seg_ptr = None
-        if threshold <= 0 or self.n_rows == 0:
-            self.long_row_threshold = 0
-            return
+        self.long_row_ids = self.long_seg_ptr = self.long_rowptr = self.long_colval = None
+        dev = self.device
         rp = rowptr_host if rowptr_host is not None else self.rowptr.cpu().numpy()
         deg = np.diff(rp.astype(np.int64))
-        long_ids = np.nonzero(deg > threshold)[0].astype(np.int32)
+        long_ids = (np.nonzero(deg > threshold)[0] if threshold > 0 else np.zeros(0, np.int64))
+        packed = torch.stack([self.col, self.val.view(torch.int32)], dim=1)     # [nnz, 2] int32
         if len(long_ids) == 0:
+            self.long_row_threshold = 0 if threshold <= 0 else self.long_row_threshold
+            self.rowptr_flagged = self.rowptr
+            self.colval = packed.contiguous()
             return
-        nseg = (deg[long_ids] + seg_len - 1) // seg_len
+        is_long = np.zeros(self.n_rows, bool)
+        is_long[long_ids] = True
+        short_deg = np.where(is_long, 0, deg)
+        rp_short = np.zeros(self.n_rows + 1, np.int64)
+        np.cumsum(short_deg, out=rp_short[1:])
+        flagged = rp_short.astype(np.uint32)
+        flagged[:-1] |= (is_long.astype(np.uint32) << np.uint32(31))
+        long_deg = deg[long_ids]
+        long_rp = np.zeros(len(long_ids) + 1, np.int32)
+        np.cumsum(long_deg, out=long_rp[1:])
+        nseg = (long_deg + seg_len - 1) // seg_len
         seg_ptr = np.zeros(len(long_ids) + 1, np.int32)
         np.cumsum(nseg, out=seg_ptr[1:])
+        # entry mask: which entries belong to long rows (device, from the row flags)
+        long_flag = torch.from_numpy(is_long).to(dev)
+        entry_long = torch.repeat_interleave(long_flag, torch.from_numpy(deg).to(dev))
+        self.colval = packed[~entry_long].contiguous()
+        self.long_colval = packed[entry_long].contiguous()
+        self.rowptr_flagged = torch.from_numpy(flagged.view(np.int32)).to(dev)
         self.n_long = int(len(long_ids))
         self.n_seg = int(seg_ptr[-1])
-        self.long_row_ids = torch.from_numpy(long_ids).to(self.device)
-        self.long_seg_ptr = torch.from_numpy(seg_ptr).to(self.device)
+        self.long_row_ids = torch.from_numpy(long_ids.astype(np.int32)).to(dev)
+        self.long_rowptr = torch.from_numpy(long_rp).to(dev)
+        self.long_seg_ptr = torch.from_numpy(seg_ptr).to(dev)
 
     def seg_ws(self, d):
         if self.n_seg == 0:

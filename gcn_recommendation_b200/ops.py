@@ -21,7 +21,7 @@ PROFILE = None
 
 
 def _launch_spmm(a, g, dev, tag):
-    n_kernels = 3 if (a.long_row_threshold > 0 and a.n_long > 0) else 1
+    n_kernels = 3 if a.n_long > 0 else 1
     COUNTERS["launches"] += n_kernels
     if PROFILE is None:
         check(_lib.load().lgcn_spmm(ctypes.byref(a), stream_ptr(dev)))
@@ -35,13 +35,14 @@ def _launch_spmm(a, g, dev, tag):
 
 def _spmm_args(g, x, mode, d):
     a = SpmmArgs()
-    a.rowptr, a.col, a.val = ptr(g.rowptr, "i32"), ptr(g.col, "i32"), ptr(g.val)
+    a.rowptr, a.colval = ptr(g.rowptr_flagged, "i32"), g.colval.data_ptr()
     a.x = ptr(x)
     a.n_rows, a.d, a.mode = g.n_rows, d, mode
-    if g.long_row_threshold > 0 and g.n_long > 0:
-        a.long_row_threshold = g.long_row_threshold
+    if g.n_long > 0:
         a.n_long = g.n_long
         a.long_row_ids = ptr(g.long_row_ids, "i32")
+        a.long_rowptr = ptr(g.long_rowptr, "i32")
+        a.long_colval = g.long_colval.data_ptr()
         a.long_seg_ptr = ptr(g.long_seg_ptr, "i32")
         a.seg_len, a.n_seg = g.seg_len, g.n_seg
         a.seg_ws = ptr(g.seg_ws(d))

@@ -33,7 +33,7 @@ typedef struct CUstream_st *lgcn_stream_t; /* == cudaStream_t */
 #define LGCN_API
 #endif
 
-#define LGCN_ABI_VERSION 1
+#define LGCN_ABI_VERSION 2
 
 #define LGCN_E_BAD_DIM   (-1) /* embedding dim not supported              */
 #define LGCN_E_BAD_ARG   (-2) /* null pointer / negative size / bad mode  */
@@ -68,41 +68,49 @@ LGCN_API int lgcn_edge_weights(const int32_t *rowptr, const int32_t *col, const 
  * autograd backward, torch.mean(torch.stack()) (lightgcn.py:54) and optimizer.step()
  * (main.py:526) when fused into the last backward hop.
  *
- * y[r,:] = sum_e val[e] * X[col[e],:]  for local rows r in [0,n_rows): rowptr is the CSR of
- * those rows, col indexes rows of X (the full table), every epilogue array is indexed by the
- * LOCAL row.  Rows no longer than the long-row threshold are accumulated as a sequential fp32
- * FMA in ascending column order (bit-equal to the CPU reference); longer rows are split into
- * segments that are summed in a fixed order (deterministic, not bit-equal).
+ * y[r,:] = sum_e val[e] * X[col[e],:]  for local rows r in [0,n_rows); col indexes rows of X
+ * (the full table), every epilogue array is indexed by the LOCAL row.
+ *
+ * Graph layout (built once per graph by the host, see graph.py: NormAdjCSR.plan):
+ *  - rows with at most `long_row_threshold` entries ("short rows") live in `colval`, an array
+ *    of packed {int32 col, float val} pairs in CSR order; rowptr[r] & 0x7fffffff is the first
+ *    entry of row r.  A short row is accumulated as a SEQUENTIAL fp32 FMA in ascending column
+ *    order -- bit-equal to the CPU reference (torch.sparse.mm).
+ *  - bit 31 of rowptr[r] marks row r as a long row: it has no entries in `colval`; its
+ *    entries live in `long_colval` (CSR over the long rows, `long_rowptr`), are cut into
+ *    segments of seg_len entries, one sub-warp per segment, partial sums staged in seg_ws and
+ *    combined in segment order (deterministic, not bit-equal to the sequential order).
  * ------------------------------------------------------------------------------------- */
+typedef struct lgcn_colval {
+    int32_t col;
+    float   val;
+} lgcn_colval;
+
 typedef struct lgcn_spmm_args {
-    const int32_t *rowptr;      /* [n_rows+1]                                         */
-    const int32_t *col;         /* [nnz]                                              */
-    const float   *val;         /* [nnz]                                              */
-    const float   *x;           /* [*, d] gathered table                              */
+    const uint32_t    *rowptr;  /* [n_rows+1] entry offsets, bit 31 = long-row flag       */
+    const lgcn_colval *colval;  /* entries of the short rows                              */
+    const float   *x;           /* [*, d] gathered table                                  */
     int64_t        n_rows;
     int32_t        d;
-    int32_t        mode;        /* LGCN_SPMM_*                                        */
-    float         *y;           /* [n_rows,d] output (modes PLAIN, ADD, MEAN)         */
-    const float   *addend;      /* ADD, ADAM: y = addend + A x ; may be NULL in ADAM  */
-    const float   *layers[8];   /* MEAN: earlier layers E_0..E_{n-1} (local rows)     */
-    int32_t        n_layers;    /* MEAN: number of entries in layers                  */
-    /* long-row plan (host-built once per graph, see graph.py): rows with more than
-     * long_row_threshold entries are cut into segments of seg_len entries, one sub-warp
-     * per segment, partial sums staged in seg_ws and combined in segment order.
-     * long_row_threshold == 0 disables the plan (every row sequential).               */
-    int32_t        long_row_threshold;
-    int32_t        n_long;      /* number of long rows                                */
-    const int32_t *long_row_ids;/* [n_long] local row ids, ascending                  */
-    const int32_t *long_seg_ptr;/* [n_long+1] first segment of each long row          */
-    int32_t        seg_len;     /* entries per segment                                */
-    int32_t        n_seg;       /* total segments == long_seg_ptr[n_long] (host copy) */
-    float         *seg_ws;      /* [long_seg_ptr[n_long], d] scratch                  */
-    /* ADAM: g = addend + A x (+ addend2) is consumed by a dense Adam update of p       */
-    const float   *addend2;     /* optional second addend (regulariser gradient)      */
-    float         *p, *m, *v;   /* [n_rows,d] parameters and Adam moments             */
-    const float   *adam_scalars;/* device [2]: step_size=lr/(1-b1^t), sqrt(1-b2^t)    */
+    int32_t        mode;        /* LGCN_SPMM_*                                            */
+    float         *y;           /* [n_rows,d] output (modes PLAIN, ADD, MEAN)             */
+    const float   *addend;      /* ADD, ADAM: y = addend + A x ; may be NULL in ADAM      */
+    const float   *layers[8];   /* MEAN: earlier layers E_0..E_{n-1} (local rows)         */
+    int32_t        n_layers;    /* MEAN: number of entries in layers                      */
+    int32_t        n_long;      /* number of long rows (0 = none)                         */
+    const int32_t *long_row_ids;/* [n_long] local row ids, ascending                      */
+    const int32_t *long_rowptr; /* [n_long+1] offsets into long_colval                    */
+    const lgcn_colval *long_colval;
+    const int32_t *long_seg_ptr;/* [n_long+1] first segment of each long row              */
+    int32_t        seg_len;     /* entries per segment                                    */
+    int32_t        n_seg;       /* total segments == long_seg_ptr[n_long] (host copy)     */
+    float         *seg_ws;      /* [n_seg, d] scratch                                     */
+    /* ADAM: g = addend + A x (+ addend2) is consumed by a dense Adam update of p           */
+    const float   *addend2;     /* optional second addend (regulariser gradient)          */
+    float         *p, *m, *v;   /* [n_rows,d] parameters and Adam moments                 */
+    const float   *adam_scalars;/* device [2]: step_size=lr/(1-b1^t), sqrt(1-b2^t)        */
     float          beta1, beta2, eps;
-    float         *g_out;       /* ADAM: optional [n_rows,d] copy of g (NULL = none)  */
+    float         *g_out;       /* ADAM: optional [n_rows,d] copy of g (NULL = none)      */
 } lgcn_spmm_args;
 
 #define LGCN_SPMM_PLAIN 0 /* y = A x                                                    */

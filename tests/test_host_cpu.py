@@ -92,18 +92,30 @@ def test_reference_on_disk_format(tmp_path):
 
 
 def test_long_row_plan_host_logic():
+    """Kernel layout of include/lgcn.h: packed {col,val} of the short rows behind a flagged
+    rowptr, long rows moved to their own CSR and cut into segments."""
     from gcn_recommendation_b200.graph import NormAdjCSR
     deg = np.array([0, 3, 70, 1, 64, 65, 200, 0], np.int64)
     rowptr = np.zeros(len(deg) + 1, np.int32)
     rowptr[1:] = np.cumsum(deg)
     nnz = int(rowptr[-1])
-    g = NormAdjCSR(torch.from_numpy(rowptr), torch.zeros(nnz, dtype=torch.int32),
-                   torch.zeros(nnz), n_cols=8, long_row_threshold=64, seg_len=32)
+    col = torch.arange(nnz, dtype=torch.int32)
+    val = torch.arange(nnz, dtype=torch.float32) * 0.5
+    g = NormAdjCSR(torch.from_numpy(rowptr), col, val, n_cols=nnz, long_row_threshold=64, seg_len=32)
     assert g.n_long == 3 and g.long_row_ids.tolist() == [2, 5, 6]
     assert g.long_seg_ptr.tolist() == [0, 3, 6, 13] and g.n_seg == 13
-    g0 = NormAdjCSR(torch.from_numpy(rowptr), torch.zeros(nnz, dtype=torch.int32),
-                    torch.zeros(nnz), n_cols=8, long_row_threshold=0)
-    assert g0.n_long == 0 and g0.long_row_threshold == 0
+    assert g.long_rowptr.tolist() == [0, 70, 135, 335]
+    flagged = g.rowptr_flagged.numpy().view(np.uint32)
+    assert (flagged >> 31).tolist() == [0, 0, 1, 0, 0, 1, 1, 0, 0]
+    assert (flagged & 0x7fffffff).tolist() == [0, 0, 3, 3, 4, 68, 68, 68, 68]
+    assert g.colval.shape == (68, 2) and g.long_colval.shape == (335, 2)
+    # short entries keep CSR order: rows 1, 3, 4
+    assert g.colval[:, 0].tolist() == list(range(0, 3)) + [73] + list(range(74, 138))
+    assert torch.equal(g.colval[:, 1].view(torch.float32), g.colval[:, 0].float() * 0.5)
+    assert g.long_colval[:70, 0].tolist() == list(range(3, 73))
+    g0 = NormAdjCSR(torch.from_numpy(rowptr), col, val, n_cols=nnz, long_row_threshold=0)
+    assert g0.n_long == 0 and g0.colval.shape == (nnz, 2)
+    assert torch.equal(g0.rowptr_flagged, g0.rowptr)
 
 
 def test_mask_csr_matches_groupby_lists():
