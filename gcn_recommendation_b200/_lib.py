@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "liblgcn_b200.so")
 c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 
 SPMM_PLAIN, SPMM_ADD, SPMM_MEAN, SPMM_ADAM = 0, 1, 2, 3
+SPMM_F_STREAM_HINTS = 1
 BPR_GP_INCLUDES_GF, BPR_NO_GRAD = 1, 2
 ABI_VERSION = 2
 
@@ -30,6 +31,7 @@ class SpmmArgs(ctypes.Structure):
         ("long_seg_ptr", c_vp), ("seg_len", c_i32), ("n_seg", c_i32), ("seg_ws", c_vp),
         ("addend2", c_vp), ("p", c_vp), ("m", c_vp), ("v", c_vp), ("adam_scalars", c_vp),
         ("beta1", c_f32), ("beta2", c_f32), ("eps", c_f32), ("g_out", c_vp),
+        ("flags", c_i32),
     ]
 
 

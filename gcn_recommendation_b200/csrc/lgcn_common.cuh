@@ -31,6 +31,51 @@ struct RowGeom {
 __device__ __forceinline__ float4 ld_nc_f4(const float *p) {
     return __ldg(reinterpret_cast<const float4 *>(p));
 }
+// L2 eviction policies (createpolicy) and loads / stores that carry them.  Tables are far
+// larger than L2 at the Amazon shape: streaming data (entries, outputs, epilogue operands) is
+// marked evict_first so it does not displace the gathered rows of high-degree columns, which
+// are marked evict_last by the graph plan (bit 31 of the packed column index).
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ld_nc_f4_hint(const float *p, uint64_t pol) {
+    float4 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float4 ld_stream_f4_hint(const float *p, uint64_t pol) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ int2 ld_stream_i2_hint(const int2 *p, uint64_t pol) {
+    int2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.s32 {%0,%1}, [%2], %3;"
+                 : "=r"(r.x), "=r"(r.y)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void st_f4_hint(float *p, const float4 &v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
+                 : "memory");
+}
 // streaming (read-once) loads: keep them out of L1
 __device__ __forceinline__ float4 ld_stream_f4(const float *p) {
     float4 r;

@@ -24,18 +24,37 @@
 namespace lgcn {
 
 constexpr int kUnroll = 8;
-constexpr int kWarps = 8;
+constexpr int kWarps = 4;
 constexpr int kThreads = kWarps * 32;
 
-template <int D>
+template <int D, int RSEL>
 struct ChunkCfg {
     using G = RowGeom<D>;
     static constexpr int RMAX = (2048 / D) < 4 ? 4 : (2048 / D);
-    static constexpr int R = G::LANES < RMAX ? G::LANES : RMAX;      // rows per worker chunk
+    static constexpr int RBIG = G::LANES < RMAX ? G::LANES : RMAX;
+    // rows per worker chunk: RSEL == 0 -> large chunks (big graphs: amortise the per-chunk
+    // pointer loads), RSEL == 1 -> 4-row chunks (small graphs: more workers, shorter chains)
+    static constexpr int R = RSEL == 0 ? RBIG : 4;
     static constexpr int WORKERS = kWarps * G::GROUPS;                // workers per CTA
     static constexpr int ROWS_PER_CTA = WORKERS * R;
+    static constexpr int UMAX = G::VEC > 1 ? 4 : 8;                   // gathers per batch
+    static constexpr int U = G::LANES < UMAX ? G::LANES : UMAX;
     static constexpr size_t SMEM = (size_t)ROWS_PER_CTA * D * sizeof(float);
 };
+
+// loads / stores of streamed (touched once) data, with or without the L2 evict_first hint
+template <bool HINT>
+__device__ __forceinline__ float4 ld_s(const float *p, uint64_t pol) {
+    return HINT ? ld_stream_f4_hint(p, pol) : ld_stream_f4(p);
+}
+template <bool HINT>
+__device__ __forceinline__ void st_s(float *p, const float4 &v, uint64_t pol) {
+    if (HINT) st_f4_hint(p, v, pol); else st_f4(p, v);
+}
+template <bool HINT>
+__device__ __forceinline__ int2 ld_cv(const int2 *p, uint64_t pol) {
+    return HINT ? ld_stream_i2_hint(p, pol) : __ldg(p);
+}
 
 // ---- epilogue for one row held in registers (long-row combine path) -----------------------
 template <int D, int MODE>
@@ -79,11 +98,11 @@ __device__ __forceinline__ void epilogue_row(const lgcn_spmm_args &a, int64_t ro
 }
 
 // ---- chunk epilogue: stream the staged rows, operand loads batched ahead of the math ------
-template <int D, int MODE>
+template <int D, int MODE, int RSEL, bool HINT>
 __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const float *stage,
-                                               int64_t r0, int nvr, unsigned long_bits) {
+                                               int64_t r0, int nvr, unsigned long_bits, uint64_t pol) {
     using G = RowGeom<D>;
-    using C = ChunkCfg<D>;
+    using C = ChunkCfg<D, RSEL>;
     const int sub = (threadIdx.x & 31) % G::LANES;
     constexpr int B = (MODE == LGCN_SPMM_ADAM || MODE == LGCN_SPMM_MEAN) ? 2 : 4;  // rows per batch
     static_assert(C::R % B == 0, "chunk rows must be a multiple of the epilogue batch");
@@ -105,17 +124,17 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
             if (MODE == LGCN_SPMM_PLAIN) {
 #pragma unroll
                 for (int i = 0; i < B; ++i)
-                    if (on[i]) st_f4(a.y + off[i], *reinterpret_cast<const float4 *>(stage + (rb + i) * D + coff));
+                    if (on[i]) st_s<HINT>(a.y + off[i], *reinterpret_cast<const float4 *>(stage + (rb + i) * D + coff), pol);
             } else if (MODE == LGCN_SPMM_ADD) {
                 float4 t[B];
 #pragma unroll
-                for (int i = 0; i < B; ++i) if (on[i]) t[i] = ld_stream_f4(a.addend + off[i]);
+                for (int i = 0; i < B; ++i) if (on[i]) t[i] = ld_s<HINT>(a.addend + off[i], pol);
 #pragma unroll
                 for (int i = 0; i < B; ++i)
                     if (on[i]) {
                         const float4 y = *reinterpret_cast<const float4 *>(stage + (rb + i) * D + coff);
                         add4(t[i], y);
-                        st_f4(a.y + off[i], t[i]);
+                        st_s<HINT>(a.y + off[i], t[i], pol);
                     }
             } else if (MODE == LGCN_SPMM_MEAN) {
                 float4 t[B][8];
@@ -123,7 +142,7 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
                 for (int i = 0; i < B; ++i)
 #pragma unroll
                     for (int l = 0; l < 8; ++l)
-                        if (on[i] && l < a.n_layers) t[i][l] = ld_stream_f4(a.layers[l] + off[i]);
+                        if (on[i] && l < a.n_layers) t[i][l] = ld_s<HINT>(a.layers[l] + off[i], pol);
 #pragma unroll
                 for (int i = 0; i < B; ++i)
                     if (on[i]) {
@@ -134,18 +153,18 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
                         add4(s, y);
                         s.x = __fdiv_rn(s.x, div); s.y = __fdiv_rn(s.y, div);
                         s.z = __fdiv_rn(s.z, div); s.w = __fdiv_rn(s.w, div);
-                        st_f4(a.y + off[i], s);
+                        st_s<HINT>(a.y + off[i], s, pol);
                     }
             } else {  // ADAM
                 float4 g[B], p[B], m[B], vv[B], g2[B];
 #pragma unroll
                 for (int i = 0; i < B; ++i)
                     if (on[i]) {
-                        if (a.addend) g[i] = ld_stream_f4(a.addend + off[i]);
-                        if (a.addend2) g2[i] = ld_stream_f4(a.addend2 + off[i]);
-                        p[i] = ld_stream_f4(a.p + off[i]);
-                        m[i] = ld_stream_f4(a.m + off[i]);
-                        vv[i] = ld_stream_f4(a.v + off[i]);
+                        if (a.addend) g[i] = ld_s<HINT>(a.addend + off[i], pol);
+                        if (a.addend2) g2[i] = ld_s<HINT>(a.addend2 + off[i], pol);
+                        p[i] = ld_s<HINT>(a.p + off[i], pol);
+                        m[i] = ld_s<HINT>(a.m + off[i], pol);
+                        vv[i] = ld_s<HINT>(a.v + off[i], pol);
                     }
 #pragma unroll
                 for (int i = 0; i < B; ++i)
@@ -154,8 +173,10 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
                         if (a.addend) add4(gr, g[i]);
                         if (a.addend2) add4(gr, g2[i]);
                         adam4(p[i], m[i], vv[i], gr, ss, bs, a.beta1, a.beta2, a.eps);
-                        st_f4(a.p + off[i], p[i]); st_f4(a.m + off[i], m[i]); st_f4(a.v + off[i], vv[i]);
-                        if (a.g_out) st_f4(a.g_out + off[i], gr);
+                        st_s<HINT>(a.p + off[i], p[i], pol);
+                        st_s<HINT>(a.m + off[i], m[i], pol);
+                        st_s<HINT>(a.v + off[i], vv[i], pol);
+                        if (a.g_out) st_s<HINT>(a.g_out + off[i], gr, pol);
                     }
             }
         }
@@ -163,10 +184,11 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
 }
 
 // ---- main kernel: one worker per chunk of R rows ---------------------------------------------
-template <int D, int MODE>
+template <int D, int MODE, int RSEL, bool HINT>
 __global__ void __launch_bounds__(kThreads) spmm_chunk_kernel(const lgcn_spmm_args a) {
     using G = RowGeom<D>;
-    using C = ChunkCfg<D>;
+    using C = ChunkCfg<D, RSEL>;
+    const uint64_t pol = HINT ? policy_evict_first() : 0ull;
     extern __shared__ __align__(16) float stage_all[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -203,7 +225,7 @@ __global__ void __launch_bounds__(kThreads) spmm_chunk_kernel(const lgcn_spmm_ar
 
     const int2 *cvp = reinterpret_cast<const int2 *>(a.colval) + chunk_beg;
     int2 cv = make_int2(0, 0);
-    if (sub < n_e) cv = __ldg(cvp + sub);
+    if (sub < n_e) cv = ld_cv<HINT>(cvp + sub, pol);
 
     float4 acc[G::VEC];
 #pragma unroll
@@ -211,24 +233,35 @@ __global__ void __launch_bounds__(kThreads) spmm_chunk_kernel(const lgcn_spmm_ar
     int cur = 0;                                          // row (within the chunk) being summed
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
+    // Batches of U gathers issued ahead of the FMAs that consume them.  (A two-deep A/B
+    // register pipeline was measured slower: 128 registers -> 16 warps/SM, and ptxas rotated
+    // the loads through temporaries.  The gather microbenchmark profiles/micro/gather_bw.cu
+    // shows ~32 KB in flight per SM already saturates HBM for 512-byte random rows.)
+    constexpr int U = C::U;
+    float4 x[U][G::VEC];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int v = 0; v < G::VEC; ++v) x[u][v] = zero4;
+
     for (int t = 0; t < max_n; t += G::LANES) {
         int2 cvn = make_int2(0, 0);
-        if (t + G::LANES + sub < n_e) cvn = __ldg(cvp + t + G::LANES + sub);   // next tile, one ahead
+        if (t + G::LANES + sub < n_e) cvn = ld_cv<HINT>(cvp + t + G::LANES + sub, pol);   // next tile, one ahead
         const int cnt = min(n_e - t, G::LANES);           // entries of this tile (may be <= 0)
         const int maxcnt = min(G::LANES, max_n - t);      // warp-uniform
-        for (int j = 0; j < maxcnt; j += kUnroll) {
-            float4 x[kUnroll][G::VEC];
+        for (int j = 0; j < maxcnt; j += U) {
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
+            for (int u = 0; u < U; ++u) {
+                // unconditional: slots past the end carry col 0 (a valid, cache-resident row).  A
+                // predicated 128-bit load makes ptxas stage through 4 temporaries and serialises
+                // the batch (ncu: stalls on the predicated MOVs).
                 const int cj = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
-                if (j + u < cnt) {
-                    const float *src = a.x + (size_t)cj * D + sub * 4;
+                const float *src = a.x + (size_t)cj * D + sub * 4;
 #pragma unroll
-                    for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
-                }
+                for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
             }
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const float wj = __int_as_float(__shfl_sync(0xffffffffu, cv.y, j + u, G::LANES));
                 const int e = chunk_beg + t + j + u;
                 // rows of this chunk that end at or before e (one ballot, no per-row pointer chase)
@@ -263,7 +296,7 @@ __global__ void __launch_bounds__(kThreads) spmm_chunk_kernel(const lgcn_spmm_ar
             for (int v = 0; v < G::VEC; ++v) st_f4(stage + r * D + sub * 4 + v * G::LANES * 4, zero4);
     }
     __syncwarp();
-    chunk_epilogue<D, MODE>(a, stage, r0, nvr, long_bits);
+    chunk_epilogue<D, MODE, RSEL, HINT>(a, stage, r0, nvr, long_bits, pol);
 }
 
 // ---- long rows: one worker per segment, partial sums to seg_ws -----------------------------
@@ -302,13 +335,18 @@ __global__ void __launch_bounds__(kThreads) spmm_long_seg_kernel(const lgcn_spmm
         for (int j = 0; j < maxcnt; j += kUnroll) {
             float4 x[kUnroll][G::VEC];
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const int cj = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
-                if (j + u < cnt) {
-                    const float *src = a.x + (size_t)cj * D + sub * 4;
+            for (int u = 0; u < kUnroll; ++u)
 #pragma unroll
-                    for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
-                }
+                for (int v = 0; v < G::VEC; ++v) x[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                // unconditional: slots past the end carry col 0 (a valid, cache-resident row).  A
+                // predicated 128-bit load makes ptxas stage through 4 temporaries and serialises
+                // the batch (ncu: stalls on the predicated MOVs).
+                const int cj = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
+                const float *src = a.x + (size_t)cj * D + sub * 4;
+#pragma unroll
+                for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
             }
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
@@ -340,42 +378,66 @@ __global__ void __launch_bounds__(kThreads) spmm_long_combine_kernel(const lgcn_
     const int s0 = __ldg(a.long_seg_ptr + i), s1 = __ldg(a.long_seg_ptr + i + 1);
     float4 acc[G::VEC];
 #pragma unroll
-    for (int v = 0; v < G::VEC; ++v)
-        acc[v] = *reinterpret_cast<const float4 *>(a.seg_ws + (size_t)s0 * D + sub * 4 +
-                                                   v * G::LANES * 4);
-    for (int s = s0 + 1; s < s1; ++s) {
+    for (int v = 0; v < G::VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // partials are summed in segment order; loads are issued 8 segments ahead of the adds
+    constexpr int CB = 8;
+    for (int s = s0; s < s1; s += CB) {
+        float4 t[CB][G::VEC];
 #pragma unroll
-        for (int v = 0; v < G::VEC; ++v) {
-            const float4 t = *reinterpret_cast<const float4 *>(a.seg_ws + (size_t)s * D + sub * 4 +
-                                                               v * G::LANES * 4);
-            add4(acc[v], t);
-        }
+        for (int k = 0; k < CB; ++k)
+            if (s + k < s1)
+#pragma unroll
+                for (int v = 0; v < G::VEC; ++v)
+                    t[k][v] = *reinterpret_cast<const float4 *>(a.seg_ws + (size_t)(s + k) * D + sub * 4 +
+                                                                 v * G::LANES * 4);
+#pragma unroll
+        for (int k = 0; k < CB; ++k)
+            if (s + k < s1) {
+#pragma unroll
+                for (int v = 0; v < G::VEC; ++v) {
+                    if (s + k == s0) acc[v] = t[k][v]; else add4(acc[v], t[k][v]);
+                }
+            }
     }
     epilogue_row<D, MODE>(a, __ldg(a.long_row_ids + i), acc);
+}
+
+template <int D, int MODE, int RSEL, bool HINT>
+static int launch_chunks(const lgcn_spmm_args &a, cudaStream_t st) {
+    using C = ChunkCfg<D, RSEL>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(spmm_chunk_kernel<D, MODE, RSEL, HINT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    const int64_t gb = (a.n_rows + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
+    if (gb > 0x7fffffffLL) return LGCN_E_TOO_LARGE;
+    spmm_chunk_kernel<D, MODE, RSEL, HINT><<<(unsigned)gb, kThreads, C::SMEM, st>>>(a);
+    LGCN_LAUNCH_CHECK();
+    return 0;
 }
 
 template <int D, int MODE>
 static int launch_mode(const lgcn_spmm_args &a, cudaStream_t st) {
     using G = RowGeom<D>;
-    using C = ChunkCfg<D>;
     constexpr int groups_per_block = kWarps * G::GROUPS;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(spmm_chunk_kernel<D, MODE>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        if (e != cudaSuccess) return (int)e;
-        attr_done = true;
-    }
     if (a.n_long > 0) {
         const unsigned gs = (unsigned)((a.n_seg + groups_per_block - 1) / groups_per_block);
         spmm_long_seg_kernel<D><<<gs, kThreads, 0, st>>>(a);
         LGCN_LAUNCH_CHECK();
     }
     if (a.n_rows > 0) {
-        const int64_t gb = (a.n_rows + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
-        if (gb > 0x7fffffffLL) return LGCN_E_TOO_LARGE;
-        spmm_chunk_kernel<D, MODE><<<(unsigned)gb, kThreads, C::SMEM, st>>>(a);
-        LGCN_LAUNCH_CHECK();
+        // small graphs: 4-row chunks so that the chip is filled (>= ~2 waves of workers)
+        const int64_t big_workers = a.n_rows / ChunkCfg<D, 0>::R;
+        const bool small = big_workers < (int64_t)kNumSMs * 32 * G::GROUPS;
+        const bool hint = (a.flags & LGCN_SPMM_F_STREAM_HINTS) != 0;
+        int rc;
+        if (small) rc = launch_chunks<D, MODE, 1, false>(a, st);
+        else if (hint) rc = launch_chunks<D, MODE, 0, true>(a, st);
+        else rc = launch_chunks<D, MODE, 0, false>(a, st);
+        if (rc) return rc;
     }
     if (a.n_long > 0) {
         const unsigned gc = (unsigned)((a.n_long + groups_per_block - 1) / groups_per_block);

@@ -17,14 +17,15 @@ from . import _lib
 
 LONG_ROW_THRESHOLD = 256
 SEG_LEN = 128
+SMALL_GRAPH_ROWS = 1_000_000
 
 
 class NormAdjCSR:
     """D^-1/2 A D^-1/2 as CSR on one GPU (rows ``[row_begin, row_begin+n_rows)`` of an
     ``n_cols``-node graph; the whole graph when not sharded)."""
 
-    def __init__(self, rowptr, col, val, n_cols, row_begin=0, long_row_threshold=LONG_ROW_THRESHOLD,
-                 seg_len=SEG_LEN, rowptr_host=None):
+    def __init__(self, rowptr, col, val, n_cols, row_begin=0, long_row_threshold=None,
+                 seg_len=None, rowptr_host=None):
         self.rowptr, self.col, self.val = rowptr, col, val
         self.n_rows = int(rowptr.numel() - 1)
         self.n_cols = int(n_cols)
@@ -32,7 +33,12 @@ class NormAdjCSR:
         self.nnz = int(col.numel())
         self.device = rowptr.device
         self._seg_ws = {}
-        self._plan_long_rows(long_row_threshold, seg_len, rowptr_host)
+        if long_row_threshold is None:
+            # small graphs are latency bound: shorter sequential chains, more workers
+            small = self.n_rows < SMALL_GRAPH_ROWS
+            long_row_threshold = LONG_ROW_THRESHOLD // 2 if small else LONG_ROW_THRESHOLD
+            seg_len = seg_len or (SEG_LEN // 2 if small else SEG_LEN)
+        self._plan_long_rows(long_row_threshold, seg_len or SEG_LEN, rowptr_host)
 
     # ---- kernel layout (once per graph) ------------------------------------------------
     def _plan_long_rows(self, threshold, seg_len, rowptr_host=None):

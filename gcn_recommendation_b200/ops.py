@@ -17,6 +17,7 @@ from ._lib import SPMM_ADAM, SPMM_ADD, SPMM_MEAN, SPMM_PLAIN, SpmmArgs, check, p
 # CUDA-event profile of the SpMM (bench.py's roofline): set PROFILE to a list to collect
 # (tag, start_event, end_event) on the launching stream.
 COUNTERS = {"launches": 0}
+L2_STREAM_BYTES = 96 << 20      # tables larger than this are streamed with L2 evict_first hints
 PROFILE = None
 
 
@@ -38,6 +39,8 @@ def _spmm_args(g, x, mode, d):
     a.rowptr, a.colval = ptr(g.rowptr_flagged, "i32"), g.colval.data_ptr()
     a.x = ptr(x)
     a.n_rows, a.d, a.mode = g.n_rows, d, mode
+    if g.n_cols * d * 4 > L2_STREAM_BYTES:
+        a.flags = _lib.SPMM_F_STREAM_HINTS
     if g.n_long > 0:
         a.n_long = g.n_long
         a.long_row_ids = ptr(g.long_row_ids, "i32")

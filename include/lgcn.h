@@ -111,7 +111,12 @@ typedef struct lgcn_spmm_args {
     const float   *adam_scalars;/* device [2]: step_size=lr/(1-b1^t), sqrt(1-b2^t)        */
     float          beta1, beta2, eps;
     float         *g_out;       /* ADAM: optional [n_rows,d] copy of g (NULL = none)      */
+    int32_t        flags;       /* LGCN_SPMM_F_*                                          */
 } lgcn_spmm_args;
+
+/* tables do not fit L2: stream entries / outputs / epilogue operands with L2 evict_first so
+ * that they do not displace the gathered rows (set by the host when n_cols*d*4 >> L2) */
+#define LGCN_SPMM_F_STREAM_HINTS 1
 
 #define LGCN_SPMM_PLAIN 0 /* y = A x                                                    */
 #define LGCN_SPMM_ADD   1 /* y = addend + A x              (Horner backward hop)        */

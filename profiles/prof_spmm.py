@@ -1,0 +1,41 @@
+"""Profiling driver: a few SpMM launches on a synthetic graph (run under ncu via gpurun).
+
+    python profiles/prof_spmm.py [workload] [mode] [launches]
+"""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gcn_recommendation_b200 import ops, synth  # noqa: E402
+from gcn_recommendation_b200.graph import NormAdjCSR  # noqa: E402
+
+workload = sys.argv[1] if len(sys.argv) > 1 else "amazon"
+mode = sys.argv[2] if len(sys.argv) > 2 else "plain"
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+dev = torch.device("cuda:0")
+U, I, B, total, d, K = synth.SHAPES[workload]
+inter = synth.generate_device(workload, dev, seed=0)
+tu, ti, _, _ = synth.split_validation_device(inter)
+g = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev)
+del inter, tu, ti
+N = U + I + B
+x = torch.randn((N, d), device=dev)
+y = torch.empty_like(x)
+add = torch.randn((N, d), device=dev) if mode != "plain" else None
+torch.cuda.synchronize()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+ev[0].record()
+for i in range(n):
+    if mode == "plain":
+        ops.spmm(g, x, out=y)
+    elif mode == "add":
+        ops.spmm(g, x, out=y, addend=add)
+    elif mode == "mean":
+        ops.spmm(g, x, out=y, mean_layers=[add, x, add, x][:K])
+    ev[i + 1].record()
+torch.cuda.synchronize()
+ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(n)]
+print(f"{workload} {mode} d={d} N={N} nnz={g.nnz} n_long={g.n_long} n_seg={g.n_seg} ms={ms}")
