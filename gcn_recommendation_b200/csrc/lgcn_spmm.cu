@@ -24,7 +24,13 @@
 namespace lgcn {
 
 constexpr int kUnroll = 8;
-constexpr int kWarps = 4;
+#ifndef LGCN_SPMM_WARPS
+#define LGCN_SPMM_WARPS 4
+#endif
+#ifndef LGCN_SPMM_MINBLOCKS
+#define LGCN_SPMM_MINBLOCKS 1
+#endif
+constexpr int kWarps = LGCN_SPMM_WARPS;
 constexpr int kThreads = kWarps * 32;
 
 template <int D, int RSEL>
@@ -185,7 +191,7 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
 
 // ---- main kernel: one worker per chunk of R rows ---------------------------------------------
 template <int D, int MODE, int RSEL, bool HINT>
-__global__ void __launch_bounds__(kThreads) spmm_chunk_kernel(const lgcn_spmm_args a) {
+__global__ void __launch_bounds__(kThreads, LGCN_SPMM_MINBLOCKS) spmm_chunk_kernel(const lgcn_spmm_args a) {
     using G = RowGeom<D>;
     using C = ChunkCfg<D, RSEL>;
     const uint64_t pol = HINT ? policy_evict_first() : 0ull;
