@@ -205,9 +205,18 @@ def run_b200(args):
     gen = torch.Generator(device=dev).manual_seed(42)
     table = xavier_uniform_table([U, I, B], d, dev, gen)
 
+    d_local = d
     if world > 1:
-        from gcn_recommendation_b200.dist import ShardedLightGCNEngine
-        eng = ShardedLightGCNEngine(csr, U, I, B, K, table, batch_size=BS)
+        from gcn_recommendation_b200.dist import FeatureShardedEngine, RowShardedEngine, column_shard
+        if args.parallelism == "feature":
+            d_local = d // world
+            local = column_shard(table, rank, world)
+            del table
+            eng = FeatureShardedEngine(csr, U, I, B, K, local, batch_size=BS)
+        else:
+            eng = RowShardedEngine(csr, U, I, B, K, table, batch_size=BS)
+            del table
+        torch.cuda.empty_cache()
     else:
         eng = LightGCNEngine(csr, U, I, B, K, table, batch_size=BS)
 
@@ -215,7 +224,7 @@ def run_b200(args):
     nb = args.steps + args.warmup
     dev_batches = make_batches(tu_h, ti_h, I, nb, 1, device=dev)
     host_batches = make_batches(tu_h, ti_h, I, nb, 2, pin=True)
-    use_graph = N < 1_000_000          # launch-bound shapes run the captured step
+    use_graph = N < 1_000_000 and world == 1     # launch-bound shapes run the captured step
 
     def barrier():
         if world > 1:
@@ -266,7 +275,7 @@ def run_b200(args):
     kernels = {}
     for tag, v in per_tag.items():
         ms = float(np.mean(v))
-        by = _spmm_bytes(g_local.n_rows if world > 1 else N, g_local.nnz, d, extra[tag])
+        by = _spmm_bytes(g_local.n_rows, g_local.nnz, d_local, extra[tag])
         kernels[tag] = {"launches": len(v), "avg_ms": ms, "algorithmic_gb": by / 1e9,
                         "achieved_gbs": by / 1e9 / (ms / 1e3)}
     peak, peak_src = _peaks()
@@ -275,7 +284,7 @@ def run_b200(args):
     tp = os.path.join(ROOT, "profiles", "spmm_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(f"{args.workload}:{dom}")
-    roofline = {"bound": "hbm", "kernel": f"spmm_rows_kernel<{d},{dom}>",
+    roofline = {"bound": "hbm", "kernel": f"spmm_chunk_kernel<{d_local},{dom}>",
                 "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_gb"] * 1e9,
@@ -294,21 +303,24 @@ def run_b200(args):
 
     # ---- full-rank eval on a sample of users ----------------------------------------------
     ev = None
-    if world == 1 and args.eval_users > 0:
+    if args.eval_users > 0 and (world == 1 or args.parallelism == "feature"):
         nu = min(args.eval_users, U)
-        eu = vu[:nu].contiguous()
-        tg = vi[:nu].contiguous()
+        nu -= nu % world
+        per = nu // world
+        eu = vu[rank * per:(rank + 1) * per].contiguous()           # this rank's users
+        tg = vi[rank * per:(rank + 1) * per].contiguous()
         mr, mc = build_mask_csr(eu.cpu().numpy(), tu_h.numpy(), ti_h.numpy(), U, dev)
         eng.evaluate(eu[:64], tg[:64], mr[:65].contiguous(), mc, 20)          # warm-up
-        torch.cuda.synchronize()
+        barrier()
         ev0.record()
         rec, ndcg, _ = eng.evaluate(eu, tg, mr, mc, 20)
         ev1.record()
-        torch.cuda.synchronize()
-        ems = ev0.elapsed_time(ev1)
+        barrier()
+        ems = max_over_ranks(ev0.elapsed_time(ev1))
         ev = {"users_per_s": nu / (ems / 1e3), "users": nu, "items": I, "ms": ems,
               "recall@20": rec, "ndcg@20": ndcg,
-              "note": "one propagation + exact fp32 score/mask/top-20 over the full catalogue"}
+              "note": "one propagation (+ all-gather of the final table when sharded) + exact fp32 "
+                      "score/mask/top-20 over the full catalogue, users sharded over the ranks"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -325,7 +337,7 @@ def run_b200(args):
             "config": {"workload": args.workload, "num_users": U, "num_items": I, "nodes": N,
                        "nnz": csr.nnz, "d": d, "layers": K, "batch": BS,
                        "steps_per_epoch": steps_per_epoch,
-                       "parallelism": "single" if world == 1 else f"row-sharded x{world}",
+                       "parallelism": "single" if world == 1 else f"{args.parallelism}-sharded x{world}",
                        "l2": "tables (%.2f GB each) are larger than L2; no flush" % (4 * N * d / 1e9)
                        if 4 * N * d > 2 * 126e6 else "working set is L2-sized: launch/L2-bound shape",
                        "cuda_graph": use_graph, "setup_s": setup_s},
@@ -349,6 +361,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="amazon", choices=sorted(CPU_SAMPLE))
     ap.add_argument("--eval-users", type=int, default=9472)
+    ap.add_argument("--parallelism", default="feature", choices=["feature", "row"],
+                    help="multi-GPU partitioning: feature columns (no propagation collectives) or "
+                         "graph rows with a per-layer all-gather (north-star layout)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

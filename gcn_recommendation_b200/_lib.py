@@ -44,6 +44,9 @@ _SIGNATURES = {
     "lgcn_sizeof_spmm_args": (ctypes.c_size_t, []),
     "lgcn_bpr_fused": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_f32,
                                       c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "lgcn_bpr_partial": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp]),
+    "lgcn_bpr_apply": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_f32,
+                                      c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "lgcn_zero_rows": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_vp]),
     "lgcn_adam_tick": (ctypes.c_int, [c_vp, c_vp, c_f32, c_f32, c_f32, c_vp]),
     "lgcn_adam": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_f32, c_f32, c_f32,

@@ -19,13 +19,16 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // D/4 lanes of the warp are active (D <= 128), or every lane owns D/128 float4 (D == 256).
-template <int D>
+// PHASE 0: fused single-GPU step.  PHASE 1: partial dots / norms only (feature-sharded tables:
+// every rank owns d/P columns) -> dots[0:bs]=<u,p>, dots[bs:2bs]=<u,n>, dots[2bs:3bs]=|.|^2.
+// PHASE 2: dots already summed over ranks; form the loss terms and scatter this rank's columns.
+template <int D, int PHASE>
 __global__ void __launch_bounds__(kBprThreads)
-bpr_fused_kernel(const float *__restrict__ F, const float *__restrict__ P,
-                 const int64_t *__restrict__ users, const int64_t *__restrict__ pos,
-                 const int64_t *__restrict__ neg, int64_t bs, int64_t item_offset, float lam,
-                 float grad_scale, int flags, float *__restrict__ sample_ws,
-                 float *__restrict__ gF, float *__restrict__ gP) {
+bpr_kernel(const float *__restrict__ F, const float *__restrict__ P,
+           const int64_t *__restrict__ users, const int64_t *__restrict__ pos,
+           const int64_t *__restrict__ neg, int64_t bs, int64_t item_offset, float lam,
+           float grad_scale, int flags, float *__restrict__ dots, float *__restrict__ sample_ws,
+           float *__restrict__ gF, float *__restrict__ gP) {
     using G = RowGeom<D>;
     const int lane = threadIdx.x & 31;
     const int64_t s = (int64_t)blockIdx.x * (kBprThreads / 32) + (threadIdx.x >> 5);
@@ -45,18 +48,27 @@ bpr_fused_kernel(const float *__restrict__ F, const float *__restrict__ P,
             ep[v] = ld_nc_f4(P + rp * D + o);
             en[v] = ld_nc_f4(P + rn * D + o);
         }
+        if (PHASE != 2) {
 #pragma unroll
-        for (int v = 0; v < G::VEC; ++v) {
-            ps += fu[v].x * fp[v].x + fu[v].y * fp[v].y + fu[v].z * fp[v].z + fu[v].w * fp[v].w;
-            ns += fu[v].x * fn[v].x + fu[v].y * fn[v].y + fu[v].z * fn[v].z + fu[v].w * fn[v].w;
-            reg += eu[v].x * eu[v].x + eu[v].y * eu[v].y + eu[v].z * eu[v].z + eu[v].w * eu[v].w;
-            reg += ep[v].x * ep[v].x + ep[v].y * ep[v].y + ep[v].z * ep[v].z + ep[v].w * ep[v].w;
-            reg += en[v].x * en[v].x + en[v].y * en[v].y + en[v].z * en[v].z + en[v].w * en[v].w;
+            for (int v = 0; v < G::VEC; ++v) {
+                ps += fu[v].x * fp[v].x + fu[v].y * fp[v].y + fu[v].z * fp[v].z + fu[v].w * fp[v].w;
+                ns += fu[v].x * fn[v].x + fu[v].y * fn[v].y + fu[v].z * fn[v].z + fu[v].w * fn[v].w;
+                reg += eu[v].x * eu[v].x + eu[v].y * eu[v].y + eu[v].z * eu[v].z + eu[v].w * eu[v].w;
+                reg += ep[v].x * ep[v].x + ep[v].y * ep[v].y + ep[v].z * ep[v].z + ep[v].w * ep[v].w;
+                reg += en[v].x * en[v].x + en[v].y * en[v].y + en[v].z * en[v].z + en[v].w * en[v].w;
+            }
         }
     }
-    ps = warp_sum(ps);
-    ns = warp_sum(ns);
-    reg = warp_sum(reg);
+    if (PHASE != 2) {
+        ps = warp_sum(ps);
+        ns = warp_sum(ns);
+        reg = warp_sum(reg);
+    }
+    if (PHASE == 1) {
+        if (lane == 0) { dots[s] = ps; dots[bs + s] = ns; dots[2 * bs + s] = reg; }
+        return;
+    }
+    if (PHASE == 2) { ps = dots[s]; ns = dots[bs + s]; reg = dots[2 * bs + s]; }
     const float x = ps - ns;                       // main.py:377-379
     const float sg = 1.0f / (1.0f + expf(-x));
     if (lane == 0) {
@@ -178,6 +190,28 @@ adam_kernel(float *__restrict__ p, const float *__restrict__ g0, const float *__
 
 }  // namespace lgcn
 
+template <int PHASE>
+static int bpr_launch(const float *F, const float *P, const int64_t *users, const int64_t *pos,
+                      const int64_t *neg, int64_t bs, int32_t d, int64_t item_offset, float lam,
+                      float grad_scale, int32_t flags, float *dots, float *sample_ws, float *gF,
+                      float *gP, cudaStream_t st) {
+    using namespace lgcn;
+    const unsigned grid = (unsigned)((bs + kBprThreads / 32 - 1) / (kBprThreads / 32));
+#define LGCN_BPR_CASE(DD)                                                                          \
+    case DD:                                                                                       \
+        bpr_kernel<DD, PHASE><<<grid, kBprThreads, 0, st>>>(F, P, users, pos, neg, bs, item_offset, \
+                                                            lam, grad_scale, flags, dots, sample_ws, \
+                                                            gF, gP);                               \
+        break;
+    switch (d) {
+        LGCN_BPR_CASE(16) LGCN_BPR_CASE(32) LGCN_BPR_CASE(64) LGCN_BPR_CASE(128) LGCN_BPR_CASE(256)
+        default: return LGCN_E_BAD_DIM;
+    }
+#undef LGCN_BPR_CASE
+    LGCN_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int lgcn_bpr_fused(const float *F, const float *P, const int64_t *users,
                               const int64_t *pos, const int64_t *neg, int64_t bs, int32_t d,
                               int64_t item_offset, float lam, float grad_scale, int32_t flags,
@@ -187,18 +221,37 @@ extern "C" int lgcn_bpr_fused(const float *F, const float *P, const int64_t *use
     if (!dim_supported(d)) return LGCN_E_BAD_DIM;
     if (bs <= 0 || !F || !P || !users || !pos || !neg || !sample_ws || !loss_out) return LGCN_E_BAD_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const unsigned grid = (unsigned)((bs + kBprThreads / 32 - 1) / (kBprThreads / 32));
-#define LGCN_BPR_CASE(DD)                                                                          \
-    case DD:                                                                                       \
-        bpr_fused_kernel<DD><<<grid, kBprThreads, 0, st>>>(F, P, users, pos, neg, bs, item_offset, \
-                                                           lam, grad_scale, flags, sample_ws, gF,  \
-                                                           gP);                                    \
-        break;
-    switch (d) {
-        LGCN_BPR_CASE(16) LGCN_BPR_CASE(32) LGCN_BPR_CASE(64) LGCN_BPR_CASE(128) LGCN_BPR_CASE(256)
-    }
-#undef LGCN_BPR_CASE
+    int rc = bpr_launch<0>(F, P, users, pos, neg, bs, d, item_offset, lam, grad_scale, flags, nullptr,
+                           sample_ws, gF, gP, st);
+    if (rc) return rc;
+    bpr_reduce_kernel<<<1, 1024, 0, st>>>(sample_ws, bs, lam, loss_out);
     LGCN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int lgcn_bpr_partial(const float *F, const float *P, const int64_t *users,
+                                const int64_t *pos, const int64_t *neg, int64_t bs, int32_t d,
+                                int64_t item_offset, float *dots, lgcn_stream_t stream) {
+    using namespace lgcn;
+    if (!dim_supported(d)) return LGCN_E_BAD_DIM;
+    if (bs <= 0 || !F || !P || !users || !pos || !neg || !dots) return LGCN_E_BAD_ARG;
+    return bpr_launch<1>(F, P, users, pos, neg, bs, d, item_offset, 0.f, 0.f, 0, dots, nullptr,
+                         nullptr, nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lgcn_bpr_apply(const float *F, const float *P, const int64_t *users,
+                              const int64_t *pos, const int64_t *neg, int64_t bs, int32_t d,
+                              int64_t item_offset, float lam, float grad_scale, int32_t flags,
+                              const float *dots, float *sample_ws, float *loss_out, float *gF,
+                              float *gP, lgcn_stream_t stream) {
+    using namespace lgcn;
+    if (!dim_supported(d)) return LGCN_E_BAD_DIM;
+    if (bs <= 0 || !F || !P || !users || !pos || !neg || !dots || !sample_ws || !loss_out)
+        return LGCN_E_BAD_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = bpr_launch<2>(F, P, users, pos, neg, bs, d, item_offset, lam, grad_scale, flags,
+                           const_cast<float *>(dots), sample_ws, gF, gP, st);
+    if (rc) return rc;
     bpr_reduce_kernel<<<1, 1024, 0, st>>>(sample_ws, bs, lam, loss_out);
     LGCN_LAUNCH_CHECK();
     return 0;

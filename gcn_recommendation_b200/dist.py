@@ -1,0 +1,165 @@
+"""Multi-GPU LightGCN: one process per GPU, ``torch.distributed`` (NCCL over NVLink) plumbing.
+
+Two partitionings of the same step (DESIGN.md "Multi-GPU"):
+
+* :class:`FeatureShardedEngine` -- every rank owns ``d/P`` feature COLUMNS of every table row
+  (parameters, Adam moments, layers, gradients) and the whole CSR.  The propagation
+  ``A_hat @ X`` is column-separable, so forward, backward and Adam need NO communication at
+  all; the only exchange is one all-reduce of ``3*batch`` partial dot products per step (the
+  BPR scores need the full feature dimension).  Evaluation all-gathers the final table once
+  and shards the users.
+* :class:`RowShardedEngine` -- the north-star layout: every rank owns a block of ROWS (of the
+  graph and of every table) and the layer input is all-gathered before each SpMM.  At the
+  Amazon shape this moves ``T*(P-1)/P`` = 6.6 GB per rank per layer over NVLink against ~1 ms
+  of local SpMM, i.e. it is communication bound; it is kept as the measured comparison.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import LgcnError
+from .engine import LightGCNEngine
+
+
+def column_shard(table, rank, world):
+    """This rank's ``d/world`` columns of a [N,d] table as a contiguous [N, d/world] tensor."""
+    d = table.shape[1]
+    if d % world or (d // world) not in (16, 32, 64, 128, 256):
+        raise LgcnError(f"d={d} cannot be split over {world} ranks (local width must be 16..256)")
+    dl = d // world
+    return table[:, rank * dl:(rank + 1) * dl].contiguous()
+
+
+class FeatureShardedEngine(LightGCNEngine):
+    """LightGCN step with the feature dimension split over the ranks of ``group``."""
+
+    def __init__(self, g, num_users, num_items, num_brands, n_layers, table_local, group=None,
+                 allreduce=None, world=None, rank=None, **kw):
+        self.group = group
+        self.world = world if world is not None else dist.get_world_size(group)
+        self.rank = rank if rank is not None else dist.get_rank(group)
+        self._allreduce = allreduce or (lambda t: dist.all_reduce(t, group=self.group))
+        super().__init__(g, num_users, num_items, num_brands, n_layers, table_local, **kw)
+        self.launches_per_step += 1
+
+    def _alloc_batch(self, bs):
+        super()._alloc_batch(bs)
+        self.dots = torch.empty(3 * bs, dtype=torch.float32, device=self.dev)
+
+    def _bpr(self, F, gp_includes_gf):
+        u, p, n = self.b_users, self.b_pos, self.b_neg
+        ops.bpr_partial(F, self.P, u, p, n, self.U, self.dots)
+        self._allreduce(self.dots)                     # the only collective of the step
+        ops.bpr_apply(F, self.P, u, p, n, self.U, self.lam, self.dots,
+                      grad_scale=1.0 / (self.K + 1), gF=self.G1, gP=self.G2,
+                      gp_includes_gf=gp_includes_gf, sample_ws=self.sample_ws, loss_out=self.loss)
+
+    def gather_final_table(self):
+        """All-gather the propagated table over the feature dimension -> [N, d] on every rank."""
+        F = self.propagate()
+        out = torch.empty((self.world,) + tuple(F.shape), dtype=F.dtype, device=F.device)
+        dist.all_gather_into_tensor(out, F.contiguous(), group=self.group)
+        return out.permute(1, 0, 2).reshape(F.shape[0], self.world * F.shape[1]).contiguous()
+
+    def evaluate(self, eval_users, targets, mask_rowptr, mask_col, k=20, batch_users=None):
+        """User-sharded full-rank evaluation (reference ``main.py:404-439``): the caller passes
+        THIS rank's users / targets / mask rows; hit and DCG sums are all-reduced."""
+        F = self.gather_final_table()
+        ids, _ = ops.score_topk(F[:self.U], F[self.U:self.U + self.I], eval_users, mask_rowptr,
+                                mask_col, k)
+        sums = torch.zeros(3, dtype=torch.float64, device=self.dev)
+        ops.eval_metrics(ids, targets, sums[:2])
+        sums[2] = eval_users.numel()
+        dist.all_reduce(sums, group=self.group)
+        s = sums.cpu().numpy()
+        return float(s[0] / s[2]), float(s[1] / s[2]), ids
+
+
+class RowShardedEngine:
+    """Row-sharded propagation with a per-layer NCCL all-gather (BASELINE.json north_star).
+
+    Rank r owns rows ``[r*rows_per_rank, (r+1)*rows_per_rank)`` of the node space padded to a
+    multiple of the world size: its CSR rows, parameters, Adam moments and layer buffers.  Before
+    every SpMM the layer input is all-gathered into a full [N_pad, d] buffer.  Each rank forms the
+    whole batch's BPR terms redundantly from the gathered table and keeps only the gradient rows
+    it owns, so the loss needs no collective.
+    """
+
+    def __init__(self, g_full, num_users, num_items, num_brands, n_layers, table_full, group=None,
+                 lr=1e-3, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, batch_size=2048):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.U, self.I, self.B = int(num_users), int(num_items), int(num_brands)
+        self.N = self.U + self.I + self.B
+        self.K = int(n_layers)
+        self.d = int(table_full.shape[1])
+        self.dev = table_full.device
+        self.lr, self.lam, self.betas, self.eps = float(lr), float(weight_decay), betas, float(eps)
+        P_ = self.world
+        self.rpr = -(-self.N // P_)                               # rows per rank (padded)
+        self.r0 = self.rank * self.rpr
+        self.r1 = min(self.N, self.r0 + self.rpr)
+        self.nloc = max(0, self.r1 - self.r0)
+        self.g = g_full.row_shard(self.r0, self.r1) if self.nloc > 0 else None
+        z = lambda: torch.zeros((self.rpr, self.d), dtype=torch.float32, device=self.dev)  # noqa: E731
+        self.P = z()
+        self.P[:self.nloc].copy_(table_full[self.r0:self.r1])
+        self.m, self.v = z(), z()
+        self.layers = [z() for _ in range(max(self.K - 1, 1))]     # local E_1..E_{K-1}
+        self.Floc = z()
+        self.G1, self.G2 = z(), z()
+        self.acc = [z(), z()]
+        full = lambda: torch.empty((self.rpr * P_, self.d), dtype=torch.float32, device=self.dev)  # noqa: E731
+        self.Xa, self.Xb = full(), full()                          # gathered tables (ping-pong)
+        self.P_full = full()
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.adam_scalars = torch.zeros(2, dtype=torch.float32, device=self.dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.bs = int(batch_size)
+        self.sample_ws = torch.empty(2 * self.bs, dtype=torch.float32, device=self.dev)
+        self.Gfull = torch.zeros((self.rpr * P_, self.d), dtype=torch.float32, device=self.dev)
+        self.G2full = torch.zeros((self.rpr * P_, self.d), dtype=torch.float32, device=self.dev)
+        per_spmm = 3 if (self.g is not None and self.g.n_long > 0) else 1
+        self.launches_per_step = 2 * self.K * per_spmm + 2 + 1 + 1
+        self.collectives_per_step = 2 * self.K
+
+    def _gather(self, local, out):
+        dist.all_gather_into_tensor(out, local, group=self.group)
+        return out
+
+    def propagate(self):
+        K = self.K
+        x = self._gather(self.P, self.P_full)                      # layer 0 on every rank
+        mean_layers = [self.P]
+        for k in range(K - 1):
+            ops.spmm(self.g, x, out=self.layers[k])
+            mean_layers.append(self.layers[k])
+            x = self._gather(self.layers[k], self.Xa if k % 2 == 0 else self.Xb)
+        ops.spmm(self.g, x, out=self.Floc, mean_layers=mean_layers)
+        return self.Floc
+
+    def bpr_step(self, users, pos, neg, use_graph=False):
+        K, U = self.K, self.U
+        dev = self.dev
+        u, p, n = users.to(dev, non_blocking=True), pos.to(dev, non_blocking=True), neg.to(dev, non_blocking=True)
+        self.propagate()
+        F_full = self._gather(self.Floc, self.Xa if (K - 1) % 2 == 0 else self.Xb)
+        # every rank forms the whole batch redundantly; gradients land in full-size scratch
+        # tables of which only the owned row block is used afterwards
+        ops.bpr_fused(F_full, self.P_full, u, p, n, U, self.lam, grad_scale=1.0 / (K + 1),
+                      gF=self.Gfull, gP=self.G2full, gp_includes_gf=True, sample_ws=self.sample_ws,
+                      loss_out=self.loss)
+        ops.adam_tick(self.step_dev, self.adam_scalars, self.lr, self.betas)
+        g1 = self.Gfull[self.r0:self.r0 + self.rpr]
+        g2 = self.G2full[self.r0:self.r0 + self.rpr]
+        x = self.Gfull                                             # acc_0 = g' is already global
+        for k in range(K - 1):
+            ops.spmm(self.g, x, out=self.acc[k % 2], addend=g1)
+            x = self._gather(self.acc[k % 2], self.Xa if k % 2 == 0 else self.Xb)
+        ops.spmm_adam(self.g, x, self.P, self.m, self.v, self.adam_scalars, addend=g2,
+                      betas=self.betas, eps=self.eps)
+        ops.zero_rows(self.Gfull, self.G2full, u, p, n, U)
+        return self.loss

@@ -147,14 +147,19 @@ class LightGCNEngine:
         U, I = self.U, self.I
         return F[:U], F[U:U + I], F[U + I:], self.P[:U], self.P[U:U + I]
 
+    def _bpr(self, F, gp_includes_gf):
+        """Loss + scatter of dL/dF (scaled by 1/(K+1)) into G1 and of the regulariser gradient
+        into G2 for the staged batch (reference ``main.py:496-497,515-525``)."""
+        ops.bpr_fused(F, self.P, self.b_users, self.b_pos, self.b_neg, self.U, self.lam,
+                      grad_scale=1.0 / (self.K + 1), gF=self.G1, gP=self.G2,
+                      gp_includes_gf=gp_includes_gf, sample_ws=self.sample_ws, loss_out=self.loss)
+
     def _step_body(self):
         g, K, U, I = self.g, self.K, self.U, self.I
         u, p, n = self.b_users, self.b_pos, self.b_neg
         F = self.propagate()
         nofus = self.fusion is None
-        ops.bpr_fused(F, self.P, u, p, n, U, self.lam, grad_scale=1.0 / (K + 1), gF=self.G1,
-                      gP=self.G2, gp_includes_gf=nofus, sample_ws=self.sample_ws,
-                      loss_out=self.loss)
+        self._bpr(F, nofus)
         ops.adam_tick(self.step_dev, self.adam_scalars, self.lr, self.betas)
         acc = self.G1
         hops = K - 1 if nofus else K

@@ -150,6 +150,38 @@ def bpr_fused(F, P, users, pos, neg, num_users, lam, grad_scale=1.0, gF=None, gP
     return loss_out
 
 
+def bpr_partial(F, P, users, pos, neg, num_users, dots):
+    """Feature-sharded step, phase 1: this rank's partial <u,p>, <u,n>, |.|^2 per sample."""
+    COUNTERS["launches"] += 1
+    check(_lib.load().lgcn_bpr_partial(ptr(F), ptr(P), ptr(users, "i64"), ptr(pos, "i64"),
+                                       ptr(neg, "i64"), users.numel(), F.shape[1], num_users,
+                                       ptr(dots), stream_ptr(F.device)))
+    return dots
+
+
+def bpr_apply(F, P, users, pos, neg, num_users, lam, dots, grad_scale=1.0, gF=None, gP=None,
+              gp_includes_gf=False, sample_ws=None, loss_out=None):
+    """Feature-sharded step, phase 2: loss from the rank-summed dots, scatter local columns."""
+    bs = users.numel()
+    dev = F.device
+    if sample_ws is None:
+        sample_ws = torch.empty(2 * bs, dtype=torch.float32, device=dev)
+    if loss_out is None:
+        loss_out = torch.empty(1, dtype=torch.float32, device=dev)
+    flags = 0
+    if gF is None and gP is None:
+        flags |= _lib.BPR_NO_GRAD
+    if gp_includes_gf:
+        flags |= _lib.BPR_GP_INCLUDES_GF
+    COUNTERS["launches"] += 2
+    check(_lib.load().lgcn_bpr_apply(ptr(F), ptr(P), ptr(users, "i64"), ptr(pos, "i64"),
+                                     ptr(neg, "i64"), bs, F.shape[1], num_users, lam, grad_scale,
+                                     flags, ptr(dots), ptr(sample_ws), ptr(loss_out),
+                                     ptr(gF, allow_none=True), ptr(gP, allow_none=True),
+                                     stream_ptr(dev)))
+    return loss_out
+
+
 def zero_rows(t0, t1, users, pos, neg, num_users):
     d = t0.shape[1]
     COUNTERS["launches"] += 1

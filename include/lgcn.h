@@ -148,6 +148,18 @@ LGCN_API int lgcn_bpr_fused(const float *F, const float *P, const int64_t *users
                    float grad_scale, int32_t flags, float *sample_ws, float *loss_out,
                    float *gF, float *gP, lgcn_stream_t stream);
 
+/* Feature-sharded tables (every rank owns d/P columns of every row): the step is split around
+ * one small all-reduce.  lgcn_bpr_partial writes this rank's partial sums dots[0:bs]=<u,p>,
+ * dots[bs:2bs]=<u,n>, dots[2bs:3bs]=|u0|^2+|p0|^2+|n0|^2; after summing dots over the ranks,
+ * lgcn_bpr_apply forms the loss and scatters this rank's gradient columns (d = local width). */
+LGCN_API int lgcn_bpr_partial(const float *F, const float *P, const int64_t *users, const int64_t *pos,
+                     const int64_t *neg, int64_t bs, int32_t d, int64_t item_offset, float *dots,
+                     lgcn_stream_t stream);
+LGCN_API int lgcn_bpr_apply(const float *F, const float *P, const int64_t *users, const int64_t *pos,
+                   const int64_t *neg, int64_t bs, int32_t d, int64_t item_offset, float lam,
+                   float grad_scale, int32_t flags, const float *dots, float *sample_ws,
+                   float *loss_out, float *gF, float *gP, lgcn_stream_t stream);
+
 /* zero the rows {u_s, io+p_s, io+n_s} of up to two [N,d] tables (undo of the scatter) */
 LGCN_API int lgcn_zero_rows(float *t0, float *t1, const int64_t *users, const int64_t *pos,
                    const int64_t *neg, int64_t bs, int32_t d, int64_t item_offset,

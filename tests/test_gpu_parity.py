@@ -403,3 +403,63 @@ def test_no_cpu_fallback(dev):
     from gcn_recommendation_b200 import _lib, ops
     with pytest.raises(_lib.LgcnError):
         ops.adam(torch.zeros(8), torch.zeros(8), torch.zeros(8), torch.zeros(8), torch.zeros(2))
+
+
+# ---------------------------------------------------------------------------- multi-GPU
+def test_feature_sharded_step_emulated_on_one_gpu(golden, dev):
+    """Feature (column) sharding: P engines over d/P columns each, the dot-product all-reduce
+    emulated by summing the ranks' partials in-process (no spin-waiting kernels, one GPU).  The
+    concatenated result must track the unsharded engine and the reference's loss curve."""
+    from gcn_recommendation_b200.dist import FeatureShardedEngine, column_shard
+    g = golden("tiny_lightgcn_d64_k3")
+    U, I, B, K = int(g["num_users"]), int(g["num_items"]), int(g["num_brands"]), int(g["K"])
+    csr = _graph(g, dev)
+    full = torch.cat([_t(g["init/user_embedding.weight"], dev), _t(g["init/item_embedding.weight"], dev),
+                      _t(g["init/brand_embedding.weight"], dev)]).contiguous()
+    world = 2
+    pending = []
+
+    def make_allreduce(r):
+        def ar(t):                      # rank 0 stashes, rank 1 sums and shares (sequential emulation)
+            pending.append(t)
+            if len(pending) == world:
+                tot = sum(pending)
+                for x in pending:
+                    x.copy_(tot)
+                pending.clear()
+        return ar
+
+    engs = [FeatureShardedEngine(csr, U, I, B, K, column_shard(full, r, world), world=world, rank=r,
+                                 allreduce=make_allreduce(r), lr=float(g["lr"]),
+                                 weight_decay=float(g["lam"]), batch_size=int(g["bs"])) for r in range(world)]
+
+    # the two "ranks" must interleave around the all-reduce: run phase by phase
+    from gcn_recommendation_b200 import ops
+    losses = []
+    for s in range(len(g["losses"])):
+        for e in engs:
+            e.b_users.copy_(_t(g["batch_users"][s], dev, torch.int64))
+            e.b_pos.copy_(_t(g["batch_pos"][s], dev, torch.int64))
+            e.b_neg.copy_(_t(g["batch_neg"][s], dev, torch.int64))
+        Fs = [e.propagate() for e in engs]
+        for e, F in zip(engs, Fs):
+            ops.bpr_partial(F, e.P, e.b_users, e.b_pos, e.b_neg, U, e.dots)
+        tot = engs[0].dots + engs[1].dots
+        for e, F in zip(engs, Fs):
+            e.dots.copy_(tot)
+            ops.bpr_apply(F, e.P, e.b_users, e.b_pos, e.b_neg, U, e.lam, e.dots, grad_scale=1.0 / (K + 1),
+                          gF=e.G1, gP=e.G2, gp_includes_gf=True, sample_ws=e.sample_ws, loss_out=e.loss)
+            ops.adam_tick(e.step_dev, e.adam_scalars, e.lr, e.betas)
+            acc = e.G1
+            for k in range(K - 1):
+                acc = ops.spmm(e.g, acc, out=e.work[k % 2], addend=e.G1)
+            ops.spmm_adam(e.g, acc, e.P, e.m, e.v, e.adam_scalars, addend=e.G2, betas=e.betas, eps=e.eps)
+            ops.zero_rows(e.G1, e.G2, e.b_users, e.b_pos, e.b_neg, U)
+        assert engs[0].loss.item() == engs[1].loss.item()
+        losses.append(engs[0].loss.item())
+    assert np.allclose(losses, g["losses"], rtol=2e-5, atol=0)
+    P = torch.cat([e.P for e in engs], dim=1).cpu().numpy()
+    ref = np.concatenate([g["final/user_embedding.weight"], g["final/item_embedding.weight"],
+                          g["final/brand_embedding.weight"]], 0)
+    mx, fro = rel_err(P, ref)
+    assert mx < 1e-3 and fro < 1e-5
