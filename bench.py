@@ -304,7 +304,7 @@ def run_b200(args):
     # ---- full-rank eval on a sample of users ----------------------------------------------
     ev = None
     if args.eval_users > 0 and (world == 1 or args.parallelism == "feature"):
-        nu = min(args.eval_users, U)
+        nu = min(args.eval_users * world, U)                         # fixed users per GPU
         nu -= nu % world
         per = nu // world
         eu = vu[rank * per:(rank + 1) * per].contiguous()           # this rank's users

@@ -57,6 +57,10 @@ _SIGNATURES = {
     "lgcn_score_topk_workspace": (ctypes.c_size_t, [c_i64, c_i64, c_i32, c_i32]),
     "lgcn_score_topk": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_i32,
                                        c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
+    "lgcn_score_tc_workspace": (ctypes.c_size_t, [c_i64, c_i64, c_i32]),
+    "lgcn_score_tc_prepare": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, ctypes.c_size_t, c_vp]),
+    "lgcn_score_tc_topk": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_i32,
+                                          c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "lgcn_eval_metrics": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
 }
 

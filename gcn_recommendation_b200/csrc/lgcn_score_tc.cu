@@ -1,0 +1,480 @@
+// lgcn_score_tc.cu -- full-rank rating on the 5th-gen tensor cores (sm_100a): tcgen05.mma with
+// TMEM accumulators, item tiles streamed by bulk async copies (TMA unit), train-item masking and
+// a per-user candidate heap fused into the epilogue, then an exact fp32 re-score.
+//
+// Replaces torch.matmul(user_batch, item_table.T) + mask loop + torch.topk of reference
+// main.py:420-426 for large catalogues.  Bit-exact ids need fp32 scores, tensor cores take
+// bf16: so this is FILTER-AND-REFINE (hard part 2):
+//
+//  1. lgcn_score_tc_prepare : item table fp32 -> bf16 in the UMMA canonical K-major layout, one
+//                             contiguous 128-item tile per bulk copy; max item norm.
+//  2. score_filter_kernel   : CTA = 128 users.  S[128 x 128] = U_bf16 . V_bf16^T per item tile
+//                             (d/16 tcgen05.mma of 128x128x16, fp32 accumulate in TMEM, two
+//                             accumulator buffers).  Epilogue threads own one user (= one TMEM
+//                             lane) each: tcgen05.ld 32 scores at a time, skip the user's train
+//                             items with a cursor into the sorted mask list, and push scores
+//                             above the user's running threshold into a C-entry min-heap in
+//                             shared memory.  The [users x items] scores never leave the SM.
+//  3. score_refine_kernel   : exact fp32 score (sequential FMA over the features, the order of
+//                             the CPU oracle) of the C candidates, ordered top-k, and a per-user
+//                             certificate: exact_kth > threshold + eps_u with eps_u an upper
+//                             bound of the bf16 rounding error; users that fail are flagged and
+//                             re-run by the exact SIMT kernel (lgcn_score.cu).
+#include <cuda_bf16.h>
+#include <float.h>
+
+#include "lgcn_common.cuh"
+
+namespace lgcn {
+namespace tc {
+
+constexpr int MT = 128;        // users per CTA (UMMA M)
+constexpr int NT = 128;        // items per tile (UMMA N)
+constexpr int NSTAGE = 3;      // item-tile ring
+constexpr int CAND = 64;       // candidates kept per user
+constexpr int kThreads = 192;  // warp 0: copy producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int TMEM_COLS = 256; // two 128-column fp32 accumulators
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, kind::f16 (bf16 in, fp32 accumulate)
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                       uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, K-major, no swizzle (canonical "interleaved" layout):
+// core matrix = 8 rows x 16 bytes stored contiguously (128 B); SBO = byte distance between 8-row
+// groups, LBO = byte distance between the two 16-byte K chunks of one K=16 instruction.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    return d;                               // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, M=128, N=128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) |
+                            ((uint32_t)(MT >> 4) << 24);
+
+// element offset of (row r, feature k) inside a canonical 128-row tile of D features
+__host__ __device__ inline int canon_off(int r, int k) {
+    return (k >> 3) * (16 * 64) + (r >> 3) * 64 + (r & 7) * 8 + (k & 7);
+}
+
+template <int D>
+struct FilterSmem {
+    __nv_bfloat16 A[MT * D];
+    __nv_bfloat16 B[NSTAGE][NT * D];
+    float heap_s[CAND][MT];
+    int heap_i[CAND][MT];
+    unsigned long long full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2];
+    uint32_t tmem_base;
+};
+
+// ---- item table -> bf16 canonical tiles, max item norm -----------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+prepare_items_kernel(const float *__restrict__ Fi, int64_t n_items, int64_t n_pad,
+                     __nv_bfloat16 *__restrict__ Bt, unsigned int *__restrict__ vmax_bits) {
+    // one thread per (item, 8-feature chunk)
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int KCH = D / 8;
+    if (idx >= n_pad * KCH) return;
+    const int64_t item = idx / KCH;
+    const int kc = (int)(idx % KCH);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (item < n_items) {
+        a = ld_stream_f4(Fi + item * D + kc * 8);
+        b = ld_stream_f4(Fi + item * D + kc * 8 + 4);
+    }
+    __nv_bfloat162 h[4];
+    h[0] = __floats2bfloat162_rn(a.x, a.y);
+    h[1] = __floats2bfloat162_rn(a.z, a.w);
+    h[2] = __floats2bfloat162_rn(b.x, b.y);
+    h[3] = __floats2bfloat162_rn(b.z, b.w);
+    const int64_t tile = item / NT;
+    const int r = (int)(item % NT);
+    __nv_bfloat16 *dst = Bt + tile * (int64_t)(NT * D) + canon_off(r, kc * 8);
+    *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(h);
+    // squared norm of the chunk, reduced over the KCH threads of the item (consecutive lanes)
+    float s = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+#pragma unroll
+    for (int off = KCH / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (kc == 0) atomicMax(vmax_bits, __float_as_uint(sqrtf(s)));   // positive floats order as uints
+}
+
+// ---- heap helpers: min-heap on (score asc, id desc) so the root is the WORST kept candidate ----
+__device__ __forceinline__ bool worse(float s, int id, float t, int tid) {
+    return s < t || (s == t && id > tid);
+}
+
+template <int D>
+__device__ __forceinline__ void heap_push(FilterSmem<D> &sm, int u, float s, int id, float &tau) {
+    int pos = 0;
+    while (true) {
+        const int l = 2 * pos + 1;
+        if (l >= CAND) break;
+        int c = l;
+        float cs = sm.heap_s[l][u];
+        int ci = sm.heap_i[l][u];
+        if (l + 1 < CAND) {
+            const float rs = sm.heap_s[l + 1][u];
+            const int ri = sm.heap_i[l + 1][u];
+            if (worse(rs, ri, cs, ci)) { c = l + 1; cs = rs; ci = ri; }
+        }
+        if (!worse(cs, ci, s, id)) break;
+        sm.heap_s[pos][u] = cs;
+        sm.heap_i[pos][u] = ci;
+        pos = c;
+    }
+    sm.heap_s[pos][u] = s;
+    sm.heap_i[pos][u] = id;
+    tau = sm.heap_s[0][u];
+}
+
+// ---- tensor-core filter ------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(kThreads, 1)
+score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ users, int64_t nu,
+                    const __nv_bfloat16 *__restrict__ Bt, int64_t n_items, int n_tiles,
+                    const int64_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_col,
+                    float *__restrict__ cand_s, int32_t *__restrict__ cand_i, float *__restrict__ tau_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FilterSmem<D> &sm = *reinterpret_cast<FilterSmem<D> *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t q0 = (int64_t)blockIdx.x * MT;
+    constexpr uint32_t TILE_BYTES = NT * D * 2;
+    constexpr uint32_t LBO = 16 * 128;     // bytes between K chunks (16 row groups of 128 B)
+    constexpr uint32_t SBO = 128;          // bytes between 8-row groups
+
+    // ---- one-time setup ------------------------------------------------------------------
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(smem_u32(&sm.full[s]), 1); mbar_init(smem_u32(&sm.empty[s]), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&sm.tfull[b]), 1); mbar_init(smem_u32(&sm.tempty[b]), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&sm.tmem_base)), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // user tile: fp32 rows -> bf16, canonical K-major layout (generic-proxy stores)
+    for (int ch = tid; ch < MT * (D / 8); ch += kThreads) {
+        const int m = ch / (D / 8), kc = ch % (D / 8);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (q0 + m < nu) {
+            const float *src = Fu + (size_t)users[q0 + m] * D + kc * 8;
+            a = ld_nc_f4(src);
+            b = ld_nc_f4(src + 4);
+        }
+        __nv_bfloat162 h[4];
+        h[0] = __floats2bfloat162_rn(a.x, a.y);
+        h[1] = __floats2bfloat162_rn(a.z, a.w);
+        h[2] = __floats2bfloat162_rn(b.x, b.y);
+        h[3] = __floats2bfloat162_rn(b.z, b.w);
+        *reinterpret_cast<uint4 *>(&sm.A[canon_off(m, kc * 8)]) = *reinterpret_cast<const uint4 *>(h);
+    }
+    for (int i = tid; i < CAND * MT; i += kThreads) {
+        sm.heap_s[i / MT][i % MT] = -FLT_MAX;
+        sm.heap_i[i / MT][i % MT] = 0x7fffffff;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> visible to UMMA
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+
+    if (warp == 0) {
+        // ===== producer: one bulk async copy (TMA unit) per 128-item tile =====
+        if (lane == 0) {
+            for (int t = 0; t < n_tiles; ++t) {
+                const int s = t % NSTAGE;
+                mbar_wait(smem_u32(&sm.empty[s]), ((t / NSTAGE) & 1) ^ 1);
+                mbar_expect_tx(smem_u32(&sm.full[s]), TILE_BYTES);
+                bulk_g2s(smem_u32(&sm.B[s][0]), Bt + (size_t)t * (NT * D), TILE_BYTES, smem_u32(&sm.full[s]));
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: a single thread drives the tensor core =====
+        if (lane == 0) {
+            const uint32_t a_base = smem_u32(&sm.A[0]);
+            for (int t = 0; t < n_tiles; ++t) {
+                const int s = t % NSTAGE, b = t & 1;
+                mbar_wait(smem_u32(&sm.tempty[b]), ((t >> 1) & 1) ^ 1);    // epilogue drained this accumulator
+                mbar_wait(smem_u32(&sm.full[s]), (t / NSTAGE) & 1);        // tile landed in smem
+                tc_fence_after();
+                const uint32_t b_base = smem_u32(&sm.B[s][0]);
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk) {
+                    const uint64_t ad = make_smem_desc(a_base + kk * 2 * LBO, LBO, SBO);
+                    const uint64_t bd = make_smem_desc(b_base + kk * 2 * LBO, LBO, SBO);
+                    tc_mma(tmem_base + b * NT, ad, bd, kIdesc, kk > 0 ? 1u : 0u);
+                }
+                tc_commit(smem_u32(&sm.empty[s]));    // smem slot reusable once these MMAs retire
+                tc_commit(smem_u32(&sm.tfull[b]));    // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===== epilogue: thread <-> user <-> TMEM lane =====
+        const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+        const int u = quad * 32 + lane;
+        const int64_t q = q0 + u;
+        float tau = -FLT_MAX;
+        int64_t mb = 0, me = 0;
+        if (mask_rowptr && q < nu) { mb = mask_rowptr[q]; me = mask_rowptr[q + 1]; }
+        int next_masked = (mb < me) ? __ldg(mask_col + mb) : 0x7fffffff;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int b = t & 1;
+            mbar_wait(smem_u32(&sm.tfull[b]), (t >> 1) & 1);
+            tc_fence_after();
+            const int tile_item0 = t * NT;
+#pragma unroll 1
+            for (int c = 0; c < NT / 32; ++c) {
+                float v[32];
+                tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * NT + c * 32), v);
+                const int item0 = tile_item0 + c * 32;
+                // the user's train items inside this 32-column window (sorted list, cursor)
+                while (next_masked < item0 + 32) {
+                    const int j = next_masked - item0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (i == j) v[i] = -FLT_MAX;
+                    ++mb;
+                    next_masked = (mb < me) ? __ldg(mask_col + mb) : 0x7fffffff;
+                }
+                if ((int64_t)item0 + 32 > n_items) {          // zero padding of the last tile
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if ((int64_t)item0 + i >= n_items) v[i] = -FLT_MAX;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (v[i] > tau) heap_push<D>(sm, u, v[i], item0 + i, tau);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sm.tempty[b]));
+        }
+        if (q < nu) {
+            for (int k = 0; k < CAND; ++k) {
+                cand_s[q * CAND + k] = sm.heap_s[k][u];
+                cand_i[q * CAND + k] = sm.heap_i[k][u];
+            }
+            tau_out[q] = tau;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// ---- exact re-score of the candidates, ordered top-k, certificate ------------------------------
+// one warp per user; lane owns candidates lane and lane+32
+__global__ void __launch_bounds__(256)
+score_refine_kernel(const float *__restrict__ Fu, const float *__restrict__ Fi,
+                    const int64_t *__restrict__ users, int64_t nu, int d,
+                    const int32_t *__restrict__ cand_i, const float *__restrict__ tau,
+                    const unsigned int *__restrict__ vmax_bits, int k, int32_t *__restrict__ out_ids,
+                    float *__restrict__ out_scores, int32_t *__restrict__ fail) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= nu) return;
+    const float *fu = Fu + (size_t)users[q] * d;
+    float sc[2];
+    int id[2];
+    float un2 = 0.f;
+    for (int j = lane; j < d; j += 32) un2 += fu[j] * fu[j];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) un2 += __shfl_xor_sync(0xffffffffu, un2, off);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        id[h] = cand_i[q * CAND + lane + 32 * h];
+        sc[h] = -FLT_MAX;
+        if (id[h] != 0x7fffffff) {
+            const float *fi = Fi + (size_t)id[h] * d;
+            float acc = 0.f;
+            for (int j = 0; j < d; j += 4) {          // sequential fp32 FMA over the features
+                const float4 a = *reinterpret_cast<const float4 *>(fu + j);
+                const float4 b = ld_nc_f4(fi + j);
+                acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc);
+                acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+            }
+            sc[h] = acc;
+        } else {
+            id[h] = -1;
+        }
+    }
+    // k rounds of warp arg-best on (score desc, id asc)
+    float kth = -FLT_MAX;
+    for (int r = 0; r < k; ++r) {
+        int hb = (sc[1] > sc[0] || (sc[1] == sc[0] && (unsigned)id[1] < (unsigned)id[0])) ? 1 : 0;
+        float bs = sc[hb];
+        int bi = id[hb];
+        int bl = lane;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float os = __shfl_xor_sync(0xffffffffu, bs, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            const int ol = __shfl_xor_sync(0xffffffffu, bl, off);
+            if (os > bs || (os == bs && (unsigned)oi < (unsigned)bi)) { bs = os; bi = oi; bl = ol; }
+        }
+        if (lane == 0) { out_ids[q * k + r] = bi; out_scores[q * k + r] = bs; }
+        if (lane == bl) sc[hb] = -FLT_MAX, id[hb] = -1;     // id -1 sorts last among -FLT_MAX ties
+        kth = bs;
+    }
+    if (lane == 0) {
+        // |bf16(u).bf16(v) - u.v| <= (2^-8 + 2^-16) |u||v| ; anything the filter dropped has an
+        // exact score <= tau + eps.  The k-th exact score must clear that bound.
+        const float vmax = __uint_as_float(*vmax_bits);
+        const float eps = 1.05f * 0.00390625f * sqrtf(un2) * vmax;
+        fail[q] = (kth > tau[q] + eps) ? 0 : 1;
+    }
+}
+
+}  // namespace tc
+}  // namespace lgcn
+
+// ---- C ABI ---------------------------------------------------------------------------------
+namespace {
+struct TcLayout {
+    size_t bt, vmax, cand_s, cand_i, tau, total;
+};
+TcLayout tc_layout(int64_t nu, int64_t n_items, int32_t d) {
+    using namespace lgcn::tc;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    TcLayout L;
+    const int64_t n_pad = (n_items + NT - 1) / NT * NT;
+    L.bt = 0;                                           // prepared item tiles (independent of nu)
+    L.vmax = up(L.bt + (size_t)n_pad * d * 2);          // max item norm (independent of nu)
+    L.cand_s = L.vmax + 256;
+    L.cand_i = up(L.cand_s + (size_t)nu * CAND * 4);
+    L.tau = up(L.cand_i + (size_t)nu * CAND * 4);
+    L.total = up(L.tau + (size_t)nu * 4);
+    return L;
+}
+}  // namespace
+
+extern "C" size_t lgcn_score_tc_workspace(int64_t nu, int64_t n_items, int32_t d) {
+    if (nu < 0 || n_items <= 0 || (d != 64 && d != 128)) return 0;
+    return tc_layout(nu, n_items, d).total;
+}
+
+extern "C" int lgcn_score_tc_prepare(const float *Fi, int64_t n_items, int32_t d, void *workspace,
+                                     size_t workspace_bytes, lgcn_stream_t stream) {
+    using namespace lgcn::tc;
+    if (d != 64 && d != 128) return LGCN_E_BAD_DIM;
+    if (!Fi || n_items <= 0 || !workspace) return LGCN_E_BAD_ARG;
+    const TcLayout L = tc_layout(0, n_items, d);
+    if (workspace_bytes < L.cand_s) return LGCN_E_BAD_ARG;
+    if (n_items > 0x7fffff00LL) return LGCN_E_TOO_LARGE;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
+    const int64_t n_pad = (n_items + NT - 1) / NT * NT;
+    unsigned int *vmax = reinterpret_cast<unsigned int *>(ws + L.vmax);
+    cudaError_t e = cudaMemsetAsync(vmax, 0, 4, st);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t threads = n_pad * (d / 8);
+    const unsigned grid = (unsigned)((threads + 255) / 256);
+    if (d == 64) prepare_items_kernel<64><<<grid, 256, 0, st>>>(Fi, n_items, n_pad, reinterpret_cast<__nv_bfloat16 *>(ws + L.bt), vmax);
+    else prepare_items_kernel<128><<<grid, 256, 0, st>>>(Fi, n_items, n_pad, reinterpret_cast<__nv_bfloat16 *>(ws + L.bt), vmax);
+    LGCN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int lgcn_score_tc_topk(const float *Fu, const float *Fi, const int64_t *users, int64_t nu,
+                                  int64_t n_items, int32_t d, const int64_t *mask_rowptr,
+                                  const int32_t *mask_col, int32_t k, int32_t *out_ids,
+                                  float *out_scores, int32_t *fail, void *workspace,
+                                  size_t workspace_bytes, lgcn_stream_t stream) {
+    using namespace lgcn::tc;
+    if (d != 64 && d != 128) return LGCN_E_BAD_DIM;
+    if (nu < 0 || n_items <= 0 || k <= 0 || k > 32 || !Fu || !Fi || !out_ids || !out_scores || !fail || !workspace)
+        return LGCN_E_BAD_ARG;
+    if (nu == 0) return 0;
+    if (!users || (mask_rowptr && !mask_col)) return LGCN_E_BAD_ARG;
+    const TcLayout L = tc_layout(nu, n_items, d);
+    if (workspace_bytes < L.total) return LGCN_E_BAD_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
+    const __nv_bfloat16 *Bt = reinterpret_cast<const __nv_bfloat16 *>(ws + L.bt);
+    float *cand_s = reinterpret_cast<float *>(ws + L.cand_s);
+    int32_t *cand_i = reinterpret_cast<int32_t *>(ws + L.cand_i);
+    float *tau = reinterpret_cast<float *>(ws + L.tau);
+    const unsigned int *vmax = reinterpret_cast<const unsigned int *>(ws + L.vmax);
+    const int n_tiles = (int)((n_items + NT - 1) / NT);
+    const unsigned grid = (unsigned)((nu + MT - 1) / MT);
+    if (d == 64) {
+        static bool done = false;
+        if (!done) {
+            cudaError_t e = cudaFuncSetAttribute(score_filter_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FilterSmem<64>));
+            if (e != cudaSuccess) return (int)e;
+            done = true;
+        }
+        score_filter_kernel<64><<<grid, kThreads, sizeof(FilterSmem<64>), st>>>(Fu, users, nu, Bt, n_items, n_tiles, mask_rowptr, mask_col, cand_s, cand_i, tau);
+    } else {
+        static bool done = false;
+        if (!done) {
+            cudaError_t e = cudaFuncSetAttribute(score_filter_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FilterSmem<128>));
+            if (e != cudaSuccess) return (int)e;
+            done = true;
+        }
+        score_filter_kernel<128><<<grid, kThreads, sizeof(FilterSmem<128>), st>>>(Fu, users, nu, Bt, n_items, n_tiles, mask_rowptr, mask_col, cand_s, cand_i, tau);
+    }
+    LGCN_LAUNCH_CHECK();
+    const unsigned rgrid = (unsigned)((nu * 32 + 255) / 256);
+    score_refine_kernel<<<rgrid, 256, 0, st>>>(Fu, Fi, users, nu, d, cand_i, tau, vmax, k, out_ids, out_scores, fail);
+    LGCN_LAUNCH_CHECK();
+    return 0;
+}

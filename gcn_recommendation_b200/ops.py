@@ -234,22 +234,73 @@ def fusion_proj_bwd(e_id, content, W, H, gH, g_eid=None, gW=None, gb=None):
     return g_eid, gW, gb
 
 
-def score_topk(F_user, F_item, users, mask_rowptr=None, mask_col=None, k=20):
-    """Full-rank scores + train mask + top-k (reference ``main.py:420-426``).
-    Returns (ids int32 [nu,k], scores fp32 [nu,k])."""
+TC_MIN_ITEMS = 8192       # below this the exact SIMT kernel is used directly
+STATS = {"tc_users": 0, "tc_fallback_users": 0}
+
+
+def score_topk_exact(F_user, F_item, users, mask_rowptr=None, mask_col=None, k=20):
+    """Exact fp32 SIMT kernel (sequential FMA scores): the reference's arithmetic."""
     nu = users.numel()
     d = F_user.shape[1]
     dev = F_user.device
     ids = torch.empty((nu, k), dtype=torch.int32, device=dev)
     sc = torch.empty((nu, k), dtype=torch.float32, device=dev)
-    lib = _lib.load()
-    wsb = lib.lgcn_score_topk_workspace(nu, F_item.shape[0], d, k)
-    ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+    if nu == 0:
+        return ids, sc
     COUNTERS["launches"] += 1
-    check(lib.lgcn_score_topk(ptr(F_user), ptr(F_item), ptr(users, "i64"), nu, F_item.shape[0], d,
-                              ptr(mask_rowptr, "i64", allow_none=True),
-                              ptr(mask_col, "i32", allow_none=True), k, ptr(ids, "i32"), ptr(sc),
-                              ws.data_ptr(), wsb, stream_ptr(dev)))
+    check(_lib.load().lgcn_score_topk(ptr(F_user), ptr(F_item), ptr(users, "i64"), nu,
+                                      F_item.shape[0], d, ptr(mask_rowptr, "i64", allow_none=True),
+                                      ptr(mask_col, "i32", allow_none=True), k, ptr(ids, "i32"),
+                                      ptr(sc), None, 0, stream_ptr(dev)))
+    return ids, sc
+
+
+def _sub_csr(rowptr, col, idx):
+    """Rows ``idx`` of a CSR (int64 rowptr) as a compact CSR (host-free torch ops)."""
+    cnt = rowptr[idx + 1] - rowptr[idx]
+    rp = torch.zeros(idx.numel() + 1, dtype=torch.int64, device=rowptr.device)
+    torch.cumsum(cnt, 0, out=rp[1:])
+    src = torch.repeat_interleave(rowptr[idx] - rp[:-1], cnt) + torch.arange(int(rp[-1].item()),
+                                                                            device=rowptr.device)
+    return rp, col[src].contiguous()
+
+
+def score_topk(F_user, F_item, users, mask_rowptr=None, mask_col=None, k=20, tensor_cores=None):
+    """Full-rank scores + train mask + top-k (reference ``main.py:420-426``).
+    Returns (ids int32 [nu,k], scores fp32 [nu,k]); ids are exactly those of fp32 sequential-FMA
+    scoring.  Large catalogues go through the tcgen05 filter + exact re-score; users whose
+    result is not certified exact are re-run by the exact kernel."""
+    nu = users.numel()
+    d = F_user.shape[1]
+    n_items = F_item.shape[0]
+    dev = F_user.device
+    if tensor_cores is None:
+        tensor_cores = d in (64, 128) and n_items >= TC_MIN_ITEMS and k <= 32
+    if not tensor_cores or nu == 0:
+        return score_topk_exact(F_user, F_item, users, mask_rowptr, mask_col, k)
+    lib = _lib.load()
+    wsb = lib.lgcn_score_tc_workspace(nu, n_items, d)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    ids = torch.empty((nu, k), dtype=torch.int32, device=dev)
+    sc = torch.empty((nu, k), dtype=torch.float32, device=dev)
+    fail = torch.empty(nu, dtype=torch.int32, device=dev)
+    st = stream_ptr(dev)
+    COUNTERS["launches"] += 3
+    check(lib.lgcn_score_tc_prepare(ptr(F_item), n_items, d, ws.data_ptr(), wsb, st))
+    check(lib.lgcn_score_tc_topk(ptr(F_user), ptr(F_item), ptr(users, "i64"), nu, n_items, d,
+                                 ptr(mask_rowptr, "i64", allow_none=True),
+                                 ptr(mask_col, "i32", allow_none=True), k, ptr(ids, "i32"), ptr(sc),
+                                 ptr(fail, "i32"), ws.data_ptr(), wsb, st))
+    bad = torch.nonzero(fail).flatten()
+    STATS["tc_users"] += nu
+    if bad.numel() > 0:                                  # not certified: exact path for those users
+        STATS["tc_fallback_users"] += int(bad.numel())
+        sub_rp = sub_col = None
+        if mask_rowptr is not None:
+            sub_rp, sub_col = _sub_csr(mask_rowptr, mask_col, bad)
+        i2, s2 = score_topk_exact(F_user, F_item, users[bad].contiguous(), sub_rp, sub_col, k)
+        ids[bad] = i2
+        sc[bad] = s2
     return ids, sc
 
 

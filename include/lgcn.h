@@ -205,6 +205,20 @@ LGCN_API int lgcn_score_topk(const float *Fu, const float *Fi, const int64_t *us
                     int64_t n_items, int32_t d, const int64_t *mask_rowptr,
                     const int32_t *mask_col, int32_t k, int32_t *out_ids, float *out_scores,
                     void *workspace, size_t workspace_bytes, lgcn_stream_t stream);
+/* Tensor-core path of the same operation for large catalogues (d = 64 or 128): a bf16
+ * tcgen05.mma filter keeps 64 candidates per user (train items skipped in the epilogue), an
+ * exact fp32 re-score orders the top k, and fail[q] = 1 marks users whose result is not
+ * CERTIFIED exact (k-th exact score within the bf16 error bound of the filter threshold);
+ * the caller re-runs those through lgcn_score_topk.  lgcn_score_tc_prepare converts the item
+ * table once per table (bf16, UMMA canonical tiles) into the head of the workspace. */
+LGCN_API size_t lgcn_score_tc_workspace(int64_t nu, int64_t n_items, int32_t d);
+LGCN_API int lgcn_score_tc_prepare(const float *Fi, int64_t n_items, int32_t d, void *workspace,
+                          size_t workspace_bytes, lgcn_stream_t stream);
+LGCN_API int lgcn_score_tc_topk(const float *Fu, const float *Fi, const int64_t *users, int64_t nu,
+                       int64_t n_items, int32_t d, const int64_t *mask_rowptr,
+                       const int32_t *mask_col, int32_t k, int32_t *out_ids, float *out_scores,
+                       int32_t *fail, void *workspace, size_t workspace_bytes,
+                       lgcn_stream_t stream);
 LGCN_API int lgcn_eval_metrics(const int32_t *topk_ids, const int64_t *targets, int64_t nu, int32_t k,
                       double *sums, lgcn_stream_t stream);
 
