@@ -318,9 +318,11 @@ def run_b200(args):
         barrier()
         ems = max_over_ranks(ev0.elapsed_time(ev1))
         ev = {"users_per_s": nu / (ems / 1e3), "users": nu, "items": I, "ms": ems,
-              "recall@20": rec, "ndcg@20": ndcg,
-              "note": "one propagation (+ all-gather of the final table when sharded) + exact fp32 "
-                      "score/mask/top-20 over the full catalogue, users sharded over the ranks"}
+              "recall@20": rec, "ndcg@20": ndcg, "tc_stats": dict(ops.STATS),
+              "scoring_tflops": 2.0 * nu * I * d / (ems / 1e3) / 1e12,
+              "note": "one propagation (+ all-gather of the final table when sharded) + tcgen05 bf16 "
+                      "filter with fused mask/top-64 + exact fp32 re-score/top-20 over the full "
+                      "catalogue, users sharded over the ranks; ms includes the propagation"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -360,7 +362,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="amazon", choices=sorted(CPU_SAMPLE))
-    ap.add_argument("--eval-users", type=int, default=9472)
+    ap.add_argument("--eval-users", type=int, default=18944)
     ap.add_argument("--parallelism", default="feature", choices=["feature", "row"],
                     help="multi-GPU partitioning: feature columns (no propagation collectives) or "
                          "graph rows with a per-layer all-gather (north-star layout)")

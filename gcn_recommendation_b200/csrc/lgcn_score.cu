@@ -42,7 +42,14 @@ __global__ void __launch_bounds__(kScoreThreads, 1)
 score_topk_kernel(const float *__restrict__ Fu, const float *__restrict__ Fi,
                   const int64_t *__restrict__ users, int64_t nu, int64_t n_items, int d,
                   const int64_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_col,
-                  int k, int32_t *__restrict__ out_ids, float *__restrict__ out_scores) {
+                  int k, int32_t *__restrict__ out_ids, float *__restrict__ out_scores,
+                  int64_t items_per_split) {
+    // blockIdx.y = item split: this CTA sweeps items [y*items_per_split, (y+1)*items_per_split)
+    // and writes its partial top-k at split offset y (merged by merge_topk_kernel).
+    const int64_t it_begin = (int64_t)blockIdx.y * items_per_split;
+    const int64_t it_end = min(n_items, it_begin + items_per_split);
+    out_ids += (size_t)blockIdx.y * nu * k;
+    out_scores += (size_t)blockIdx.y * nu * k;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScoreSmem &sm = *reinterpret_cast<ScoreSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -62,7 +69,7 @@ score_topk_kernel(const float *__restrict__ Fu, const float *__restrict__ Fi,
     }
     __syncthreads();
 
-    for (int64_t it0 = 0; it0 < n_items; it0 += TI) {
+    for (int64_t it0 = it_begin; it0 < it_end; it0 += TI) {
         float acc[8][4];
 #pragma unroll
         for (int a = 0; a < 8; ++a)
@@ -87,7 +94,7 @@ score_topk_kernel(const float *__restrict__ Fu, const float *__restrict__ Fi,
                 const int i = idx % TI, jq = idx / TI;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 const int64_t item = it0 + i;
-                if (item < n_items && jq * 4 < kc) v = ld_nc_f4(Fi + (size_t)item * d + k0 + jq * 4);
+                if (item < it_end && jq * 4 < kc) v = ld_nc_f4(Fi + (size_t)item * d + k0 + jq * 4);
                 sm.Bs[jq * 4 + 0][i] = v.x;
                 sm.Bs[jq * 4 + 1][i] = v.y;
                 sm.Bs[jq * 4 + 2][i] = v.z;
@@ -117,7 +124,7 @@ score_topk_kernel(const float *__restrict__ Fu, const float *__restrict__ Fi,
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int64_t item = it0 + tx * 4 + c;
-                if (item < n_items && acc[a][c] > th) {
+                if (item < it_end && acc[a][c] > th) {
                     const int slot = atomicAdd(&sm.q_cnt[u], 1);
                     sm.q_s[u][slot] = acc[a][c];
                     sm.q_i[u][slot] = (int)item;
@@ -173,6 +180,51 @@ score_topk_kernel(const float *__restrict__ Fu, const float *__restrict__ Fi,
     }
 }
 
+// merge the per-split partial top-k lists of one user (exact scores: the merge is exact)
+__global__ void __launch_bounds__(256)
+merge_topk_kernel(const int32_t *__restrict__ p_ids, const float *__restrict__ p_sc, int64_t nu, int k,
+                  int n_splits, int32_t *__restrict__ out_ids, float *__restrict__ out_scores) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= nu) return;
+    const int total = n_splits * k;
+    // every split list is sorted best-first: lane l walks lists l, l+32, ... with a cursor each
+    constexpr int MAXL = 4;                       // n_splits <= 128
+    int cur[MAXL];
+#pragma unroll
+    for (int j = 0; j < MAXL; ++j) cur[j] = 0;
+    (void)total;
+    for (int r = 0; r < k; ++r) {
+        float bs = -FLT_MAX;
+        int bi = -1, bj = -1;
+#pragma unroll
+        for (int j = 0; j < MAXL; ++j) {
+            const int sp = lane + 32 * j;
+            if (sp < n_splits && cur[j] < k) {
+                const size_t o = ((size_t)sp * nu + q) * k + cur[j];
+                const float s = p_sc[o];
+                const int id = p_ids[o];
+                if (id >= 0 && (bj < 0 || better(s, id, bs, bi))) { bs = s; bi = id; bj = j; }
+            }
+        }
+        float ws = bs;
+        int wi = bi, wl = lane;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float os = __shfl_xor_sync(0xffffffffu, ws, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, wi, off);
+            const int ol = __shfl_xor_sync(0xffffffffu, wl, off);
+            const bool take = oi >= 0 && (wi < 0 || better(os, oi, ws, wi));
+            if (take) { ws = os; wi = oi; wl = ol; }
+        }
+        if (lane == 0) { out_ids[q * k + r] = wi; out_scores[q * k + r] = wi >= 0 ? ws : -FLT_MAX; }
+        if (lane == wl && bj >= 0 && wi >= 0) {
+#pragma unroll
+            for (int j = 0; j < MAXL; ++j) if (j == bj) ++cur[j];
+        }
+    }
+}
+
 // hits and DCG of reference main.py:430-438: one thread per evaluated user
 __global__ void eval_metrics_kernel(const int32_t *__restrict__ ids, const int64_t *__restrict__ targets,
                                     int64_t nu, int k, double *__restrict__ sums) {
@@ -200,9 +252,24 @@ __global__ void eval_metrics_kernel(const int32_t *__restrict__ ids, const int64
 
 }  // namespace lgcn
 
+namespace {
+// item splits so that a small number of user tiles still fills the chip
+int choose_splits(int64_t nu, int64_t n_items) {
+    const int64_t user_tiles = (nu + lgcn::TU - 1) / lgcn::TU;
+    if (user_tiles >= 2 * lgcn::kNumSMs || n_items < 64 * lgcn::TI) return 1;
+    int64_t s = (2 * lgcn::kNumSMs + user_tiles - 1) / user_tiles;
+    const int64_t max_by_items = n_items / (16 * lgcn::TI);
+    if (s > max_by_items) s = max_by_items;
+    if (s > 128) s = 128;
+    return s < 1 ? 1 : (int)s;
+}
+}  // namespace
+
 extern "C" size_t lgcn_score_topk_workspace(int64_t nu, int64_t n_items, int32_t d, int32_t k) {
-    (void)nu; (void)n_items; (void)d; (void)k;
-    return 0;   // the exact path keeps all state in shared memory
+    (void)d;
+    if (nu <= 0 || n_items <= 0 || k <= 0) return 0;
+    const int s = choose_splits(nu, n_items);
+    return s <= 1 ? 0 : (size_t)s * nu * k * 8;
 }
 
 extern "C" int lgcn_score_topk(const float *Fu, const float *Fi, const int64_t *users, int64_t nu,
@@ -211,7 +278,6 @@ extern "C" int lgcn_score_topk(const float *Fu, const float *Fi, const int64_t *
                                float *out_scores, void *workspace, size_t workspace_bytes,
                                lgcn_stream_t stream) {
     using namespace lgcn;
-    (void)workspace; (void)workspace_bytes;
     if (d <= 0 || d % 4 != 0) return LGCN_E_BAD_DIM;
     if (nu < 0 || n_items <= 0 || k <= 0 || k > KMAX || !Fu || !Fi || !out_ids || !out_scores)
         return LGCN_E_BAD_ARG;
@@ -229,8 +295,25 @@ extern "C" int lgcn_score_topk(const float *Fu, const float *Fi, const int64_t *
     }
     const int64_t blocks = (nu + TU - 1) / TU;
     if (blocks > 0x7fffffffLL) return LGCN_E_TOO_LARGE;
-    score_topk_kernel<<<(unsigned)blocks, kScoreThreads, sizeof(ScoreSmem), st>>>(
-        Fu, Fi, users, nu, n_items, d, mask_rowptr, mask_col, k, out_ids, out_scores);
+    int splits = choose_splits(nu, n_items);
+    if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * nu * k * 8)) splits = 1;
+    if (splits == 1) {
+        score_topk_kernel<<<(unsigned)blocks, kScoreThreads, sizeof(ScoreSmem), st>>>(
+            Fu, Fi, users, nu, n_items, d, mask_rowptr, mask_col, k, out_ids, out_scores, n_items);
+        LGCN_LAUNCH_CHECK();
+        return 0;
+    }
+    int64_t per = (n_items + splits - 1) / splits;
+    per = (per + TI - 1) / TI * TI;
+    splits = (int)((n_items + per - 1) / per);
+    int32_t *p_ids = reinterpret_cast<int32_t *>(workspace);
+    float *p_sc = reinterpret_cast<float *>(p_ids + (size_t)splits * nu * k);
+    dim3 grid((unsigned)blocks, (unsigned)splits);
+    score_topk_kernel<<<grid, kScoreThreads, sizeof(ScoreSmem), st>>>(
+        Fu, Fi, users, nu, n_items, d, mask_rowptr, mask_col, k, p_ids, p_sc, per);
+    LGCN_LAUNCH_CHECK();
+    merge_topk_kernel<<<(unsigned)((nu * 32 + 255) / 256), 256, 0, st>>>(p_ids, p_sc, nu, k, splits, out_ids,
+                                                                           out_scores);
     LGCN_LAUNCH_CHECK();
     return 0;
 }

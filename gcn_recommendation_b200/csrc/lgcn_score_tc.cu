@@ -30,10 +30,13 @@ namespace tc {
 
 constexpr int MT = 128;        // users per CTA (UMMA M)
 constexpr int NT = 128;        // items per tile (UMMA N)
-constexpr int NSTAGE = 3;      // item-tile ring
-constexpr int CAND = 64;       // candidates kept per user
-constexpr int kThreads = 192;  // warp 0: copy producer, warp 1: MMA issuer, warps 2-5: epilogue
-constexpr int TMEM_COLS = 256; // two 128-column fp32 accumulators
+constexpr int NSTAGE = 2;      // item-tile ring
+constexpr int CAND = 128;      // candidates kept per user (all epilogue groups together)
+constexpr int NB = 4;          // TMEM accumulator buffers == epilogue groups (tile t -> group t % NB)
+constexpr int GCAND = CAND / NB;             // heap entries per (user, group)
+constexpr int kThreads = 64 + NB * 128;      // warp 0: copy producer, warp 1: MMA issuer, then NB
+                                             // epilogue groups of 4 warps (one per TMEM lane quadrant)
+constexpr int TMEM_COLS = NB * 128;          // NB 128-column fp32 accumulators (all 512 columns)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -75,9 +78,9 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (asynchronous: the values
+// are valid after tc_ld_wait)
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -87,10 +90,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, no swizzle (canonical "interleaved" layout):
 // core matrix = 8 rows x 16 bytes stored contiguously (128 B); SBO = byte distance between 8-row
@@ -116,9 +117,9 @@ template <int D>
 struct FilterSmem {
     __nv_bfloat16 A[MT * D];
     __nv_bfloat16 B[NSTAGE][NT * D];
-    float heap_s[CAND][MT];
-    int heap_i[CAND][MT];
-    unsigned long long full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2];
+    float heap_s[NB][GCAND][MT];
+    int heap_i[NB][GCAND][MT];
+    unsigned long long full[NSTAGE], empty[NSTAGE], tfull[NB], tempty[NB];
     uint32_t tmem_base;
 };
 
@@ -159,28 +160,30 @@ __device__ __forceinline__ bool worse(float s, int id, float t, int tid) {
     return s < t || (s == t && id > tid);
 }
 
-template <int D>
-__device__ __forceinline__ void heap_push(FilterSmem<D> &sm, int u, float s, int id, float &tau) {
+// Replace the root (worst kept candidate) of user u's min-heap and sift down.  NOT inlined: it is
+// called from 32 sites per 32-column window and runs ~1e-4 of the time; inlining it made the
+// epilogue loop ~200 KB of code and instruction-cache bound (measured: 9200 cycles per tile).
+__device__ __noinline__ float heap_push(float *heap_s, int *heap_i, int u, float s, int id) {
     int pos = 0;
     while (true) {
         const int l = 2 * pos + 1;
-        if (l >= CAND) break;
+        if (l >= GCAND) break;
         int c = l;
-        float cs = sm.heap_s[l][u];
-        int ci = sm.heap_i[l][u];
-        if (l + 1 < CAND) {
-            const float rs = sm.heap_s[l + 1][u];
-            const int ri = sm.heap_i[l + 1][u];
+        float cs = heap_s[l * MT + u];
+        int ci = heap_i[l * MT + u];
+        if (l + 1 < GCAND) {
+            const float rs = heap_s[(l + 1) * MT + u];
+            const int ri = heap_i[(l + 1) * MT + u];
             if (worse(rs, ri, cs, ci)) { c = l + 1; cs = rs; ci = ri; }
         }
         if (!worse(cs, ci, s, id)) break;
-        sm.heap_s[pos][u] = cs;
-        sm.heap_i[pos][u] = ci;
+        heap_s[pos * MT + u] = cs;
+        heap_i[pos * MT + u] = ci;
         pos = c;
     }
-    sm.heap_s[pos][u] = s;
-    sm.heap_i[pos][u] = id;
-    tau = sm.heap_s[0][u];
+    heap_s[pos * MT + u] = s;
+    heap_i[pos * MT + u] = id;
+    return heap_s[u];                     // new threshold = score of the root
 }
 
 // ---- tensor-core filter ------------------------------------------------------------------------
@@ -201,7 +204,7 @@ score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ us
     // ---- one-time setup ------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(smem_u32(&sm.full[s]), 1); mbar_init(smem_u32(&sm.empty[s]), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&sm.tfull[b]), 1); mbar_init(smem_u32(&sm.tempty[b]), 4); }
+        for (int b = 0; b < NB; ++b) { mbar_init(smem_u32(&sm.tfull[b]), 1); mbar_init(smem_u32(&sm.tempty[b]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -226,8 +229,8 @@ score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ us
         *reinterpret_cast<uint4 *>(&sm.A[canon_off(m, kc * 8)]) = *reinterpret_cast<const uint4 *>(h);
     }
     for (int i = tid; i < CAND * MT; i += kThreads) {
-        sm.heap_s[i / MT][i % MT] = -FLT_MAX;
-        sm.heap_i[i / MT][i % MT] = 0x7fffffff;
+        (&sm.heap_s[0][0][0])[i] = -FLT_MAX;
+        (&sm.heap_i[0][0][0])[i] = 0x7fffffff;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> visible to UMMA
     tc_fence_before();
@@ -250,8 +253,8 @@ score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ us
         if (lane == 0) {
             const uint32_t a_base = smem_u32(&sm.A[0]);
             for (int t = 0; t < n_tiles; ++t) {
-                const int s = t % NSTAGE, b = t & 1;
-                mbar_wait(smem_u32(&sm.tempty[b]), ((t >> 1) & 1) ^ 1);    // epilogue drained this accumulator
+                const int s = t % NSTAGE, b = t % NB;
+                mbar_wait(smem_u32(&sm.tempty[b]), ((t / NB) & 1) ^ 1);    // epilogue drained this accumulator
                 mbar_wait(smem_u32(&sm.full[s]), (t / NSTAGE) & 1);        // tile landed in smem
                 tc_fence_after();
                 const uint32_t b_base = smem_u32(&sm.B[s][0]);
@@ -266,23 +269,32 @@ score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ us
             }
         }
     } else {
-        // ===== epilogue: thread <-> user <-> TMEM lane =====
+        // ===== epilogue: group g owns tiles t = g (mod NB); thread <-> user <-> TMEM lane =====
+        const int g = (warp - 2) >> 2;                // epilogue group == accumulator buffer
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
         const int u = quad * 32 + lane;
         const int64_t q = q0 + u;
+        float *hs = &sm.heap_s[g][0][0];
+        int *hi = &sm.heap_i[g][0][0];
         float tau = -FLT_MAX;
         int64_t mb = 0, me = 0;
         if (mask_rowptr && q < nu) { mb = mask_rowptr[q]; me = mask_rowptr[q + 1]; }
-        int next_masked = (mb < me) ? __ldg(mask_col + mb) : 0x7fffffff;
-        for (int t = 0; t < n_tiles; ++t) {
-            const int b = t & 1;
-            mbar_wait(smem_u32(&sm.tfull[b]), (t >> 1) & 1);
+        int next_masked = 0x7fffffff;
+        for (int t = g; t < n_tiles; t += NB) {
+            mbar_wait(smem_u32(&sm.tfull[g]), ((t / NB) & 1));
             tc_fence_after();
             const int tile_item0 = t * NT;
+            // this group sees every NB-th tile: advance the mask cursor to the tile start
+            while (mb < me && __ldg(mask_col + mb) < tile_item0) ++mb;
+            next_masked = (mb < me) ? __ldg(mask_col + mb) : 0x7fffffff;
 #pragma unroll 1
             for (int c = 0; c < NT / 32; ++c) {
+                uint32_t raw[32];
+                tc_ld32_issue(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * NT + c * 32), raw);
+                tc_ld_wait();
                 float v[32];
-                tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * NT + c * 32), v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
                 const int item0 = tile_item0 + c * 32;
                 // the user's train items inside this 32-column window (sorted list, cursor)
                 while (next_masked < item0 + 32) {
@@ -296,20 +308,31 @@ score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ us
 #pragma unroll
                     for (int i = 0; i < 32; ++i) if ((int64_t)item0 + i >= n_items) v[i] = -FLT_MAX;
                 }
+                // window maximum as a balanced tree (a 31-deep FMNMX chain is latency bound)
+                float m16[16], m8[8], m4[4];
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (v[i] > tau) heap_push<D>(sm, u, v[i], item0 + i, tau);
+                for (int i = 0; i < 16; ++i) m16[i] = fmaxf(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) m8[i] = fmaxf(m16[2 * i], m16[2 * i + 1]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) m4[i] = fmaxf(m8[2 * i], m8[2 * i + 1]);
+                const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                if (mx > tau) {                               // rare once the heap has warmed up
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (v[i] > tau) tau = heap_push(hs, hi, u, v[i], item0 + i);
+                }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&sm.tempty[b]));
+            if (lane == 0) mbar_arrive(smem_u32(&sm.tempty[g]));
         }
         if (q < nu) {
-            for (int k = 0; k < CAND; ++k) {
-                cand_s[q * CAND + k] = sm.heap_s[k][u];
-                cand_i[q * CAND + k] = sm.heap_i[k][u];
+            for (int k = 0; k < GCAND; ++k) {
+                cand_s[q * CAND + g * GCAND + k] = hs[k * MT + u];
+                cand_i[q * CAND + g * GCAND + k] = hi[k * MT + u];
             }
-            tau_out[q] = tau;
+            tau_out[q * NB + g] = tau;
         }
     }
     tc_fence_before();
@@ -332,14 +355,15 @@ score_refine_kernel(const float *__restrict__ Fu, const float *__restrict__ Fi,
     const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= nu) return;
     const float *fu = Fu + (size_t)users[q] * d;
-    float sc[2];
-    int id[2];
+    constexpr int CPL = CAND / 32;                 // candidates per lane
+    float sc[CPL];
+    int id[CPL];
     float un2 = 0.f;
     for (int j = lane; j < d; j += 32) un2 += fu[j] * fu[j];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) un2 += __shfl_xor_sync(0xffffffffu, un2, off);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < CPL; ++h) {
         id[h] = cand_i[q * CAND + lane + 32 * h];
         sc[h] = -FLT_MAX;
         if (id[h] != 0x7fffffff) {
@@ -359,9 +383,14 @@ score_refine_kernel(const float *__restrict__ Fu, const float *__restrict__ Fi,
     // k rounds of warp arg-best on (score desc, id asc)
     float kth = -FLT_MAX;
     for (int r = 0; r < k; ++r) {
-        int hb = (sc[1] > sc[0] || (sc[1] == sc[0] && (unsigned)id[1] < (unsigned)id[0])) ? 1 : 0;
-        float bs = sc[hb];
-        int bi = id[hb];
+        int hb = 0;
+#pragma unroll
+        for (int h = 1; h < CPL; ++h)
+            if (sc[h] > sc[hb] || (sc[h] == sc[hb] && (unsigned)id[h] < (unsigned)id[hb])) hb = h;
+        float bs = sc[0];
+        int bi = id[0];
+#pragma unroll
+        for (int h = 1; h < CPL; ++h) if (h == hb) { bs = sc[h]; bi = id[h]; }
         int bl = lane;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
@@ -371,7 +400,10 @@ score_refine_kernel(const float *__restrict__ Fu, const float *__restrict__ Fi,
             if (os > bs || (os == bs && (unsigned)oi < (unsigned)bi)) { bs = os; bi = oi; bl = ol; }
         }
         if (lane == 0) { out_ids[q * k + r] = bi; out_scores[q * k + r] = bs; }
-        if (lane == bl) sc[hb] = -FLT_MAX, id[hb] = -1;     // id -1 sorts last among -FLT_MAX ties
+        if (lane == bl) {                                   // id -1 sorts last among -FLT_MAX ties
+#pragma unroll
+            for (int h = 0; h < CPL; ++h) if (h == hb) { sc[h] = -FLT_MAX; id[h] = -1; }
+        }
         kth = bs;
     }
     if (lane == 0) {
@@ -379,7 +411,10 @@ score_refine_kernel(const float *__restrict__ Fu, const float *__restrict__ Fi,
         // exact score <= tau + eps.  The k-th exact score must clear that bound.
         const float vmax = __uint_as_float(*vmax_bits);
         const float eps = 1.05f * 0.00390625f * sqrtf(un2) * vmax;
-        fail[q] = (kth > tau[q] + eps) ? 0 : 1;
+        float tq = tau[q * NB];
+#pragma unroll
+        for (int g = 1; g < NB; ++g) tq = fmaxf(tq, tau[q * NB + g]);
+        fail[q] = (kth > tq + eps) ? 0 : 1;
     }
 }
 
@@ -401,7 +436,7 @@ TcLayout tc_layout(int64_t nu, int64_t n_items, int32_t d) {
     L.cand_s = L.vmax + 256;
     L.cand_i = up(L.cand_s + (size_t)nu * CAND * 4);
     L.tau = up(L.cand_i + (size_t)nu * CAND * 4);
-    L.total = up(L.tau + (size_t)nu * 4);
+    L.total = up(L.tau + (size_t)nu * 4 * lgcn::tc::NB);
     return L;
 }
 }  // namespace

@@ -247,11 +247,14 @@ def score_topk_exact(F_user, F_item, users, mask_rowptr=None, mask_col=None, k=2
     sc = torch.empty((nu, k), dtype=torch.float32, device=dev)
     if nu == 0:
         return ids, sc
-    COUNTERS["launches"] += 1
-    check(_lib.load().lgcn_score_topk(ptr(F_user), ptr(F_item), ptr(users, "i64"), nu,
-                                      F_item.shape[0], d, ptr(mask_rowptr, "i64", allow_none=True),
-                                      ptr(mask_col, "i32", allow_none=True), k, ptr(ids, "i32"),
-                                      ptr(sc), None, 0, stream_ptr(dev)))
+    lib = _lib.load()
+    wsb = lib.lgcn_score_topk_workspace(nu, F_item.shape[0], d, k)
+    ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+    COUNTERS["launches"] += 2 if wsb else 1
+    check(lib.lgcn_score_topk(ptr(F_user), ptr(F_item), ptr(users, "i64"), nu,
+                              F_item.shape[0], d, ptr(mask_rowptr, "i64", allow_none=True),
+                              ptr(mask_col, "i32", allow_none=True), k, ptr(ids, "i32"),
+                              ptr(sc), ws.data_ptr(), wsb, stream_ptr(dev)))
     return ids, sc
 
 
@@ -286,11 +289,20 @@ def score_topk(F_user, F_item, users, mask_rowptr=None, mask_col=None, k=20, ten
     fail = torch.empty(nu, dtype=torch.int32, device=dev)
     st = stream_ptr(dev)
     COUNTERS["launches"] += 3
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if PROFILE is not None else None
+    if ev:
+        ev[0].record()
     check(lib.lgcn_score_tc_prepare(ptr(F_item), n_items, d, ws.data_ptr(), wsb, st))
+    if ev:
+        ev[1].record()
     check(lib.lgcn_score_tc_topk(ptr(F_user), ptr(F_item), ptr(users, "i64"), nu, n_items, d,
                                  ptr(mask_rowptr, "i64", allow_none=True),
                                  ptr(mask_col, "i32", allow_none=True), k, ptr(ids, "i32"), ptr(sc),
                                  ptr(fail, "i32"), ws.data_ptr(), wsb, st))
+    if ev:
+        ev[2].record()
+        PROFILE.append(("score_tc_prepare", ev[0], ev[1]))
+        PROFILE.append(("score_tc_filter_refine", ev[1], ev[2]))
     bad = torch.nonzero(fail).flatten()
     STATS["tc_users"] += nu
     if bad.numel() > 0:                                  # not certified: exact path for those users
