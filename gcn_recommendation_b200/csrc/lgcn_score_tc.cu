@@ -279,14 +279,16 @@ score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ us
         float tau = -FLT_MAX;
         int64_t mb = 0, me = 0;
         if (mask_rowptr && q < nu) { mb = mask_rowptr[q]; me = mask_rowptr[q + 1]; }
-        int next_masked = 0x7fffffff;
+        int next_masked = (mb < me) ? __ldg(mask_col + mb) : 0x7fffffff;
         for (int t = g; t < n_tiles; t += NB) {
             mbar_wait(smem_u32(&sm.tfull[g]), ((t / NB) & 1));
             tc_fence_after();
             const int tile_item0 = t * NT;
             // this group sees every NB-th tile: advance the mask cursor to the tile start
-            while (mb < me && __ldg(mask_col + mb) < tile_item0) ++mb;
-            next_masked = (mb < me) ? __ldg(mask_col + mb) : 0x7fffffff;
+            while (next_masked < tile_item0) {            // register compare; loads only on advance
+                ++mb;
+                next_masked = (mb < me) ? __ldg(mask_col + mb) : 0x7fffffff;
+            }
 #pragma unroll 1
             for (int c = 0; c < NT / 32; ++c) {
                 uint32_t raw[32];

@@ -63,10 +63,12 @@ class FeatureShardedEngine(LightGCNEngine):
         dist.all_gather_into_tensor(out, F.contiguous(), group=self.group)
         return out.permute(1, 0, 2).reshape(F.shape[0], self.world * F.shape[1]).contiguous()
 
-    def evaluate(self, eval_users, targets, mask_rowptr, mask_col, k=20, batch_users=None):
+    def evaluate(self, eval_users, targets, mask_rowptr, mask_col, k=20, propagate=True):
         """User-sharded full-rank evaluation (reference ``main.py:404-439``): the caller passes
         THIS rank's users / targets / mask rows; hit and DCG sums are all-reduced."""
-        F = self.gather_final_table()
+        if propagate or getattr(self, "_F_full", None) is None:
+            self._F_full = self.gather_final_table()
+        F = self._F_full
         ids, _ = ops.score_topk(F[:self.U], F[self.U:self.U + self.I], eval_users, mask_rowptr,
                                 mask_col, k)
         sums = torch.zeros(3, dtype=torch.float64, device=self.dev)

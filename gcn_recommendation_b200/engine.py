@@ -247,9 +247,10 @@ class LightGCNEngine:
         F = self.propagate() if propagate else self.F
         return ops.score_topk(F[:self.U], F[self.U:self.U + self.I], users, mask_rowptr, mask_col, k)
 
-    def evaluate(self, eval_users, targets, mask_rowptr, mask_col, k=20, batch_users=None):
+    def evaluate(self, eval_users, targets, mask_rowptr, mask_col, k=20, propagate=True):
         """recall@k / NDCG@k as reference ``main.py:404-439``.  Returns (recall, ndcg, ids)."""
-        self.propagate()
+        if propagate:
+            self.propagate()
         nu = eval_users.numel()
         sums = torch.zeros(2, dtype=torch.float64, device=self.dev)
         ids, _ = self.rate_topk(eval_users, mask_rowptr, mask_col, k, propagate=False)
