@@ -218,7 +218,15 @@ def run_b200(args):
             del table
         torch.cuda.empty_cache()
     else:
-        eng = LightGCNEngine(csr, U, I, B, K, table, batch_size=BS)
+        fusion = None
+        if args.fusion:
+            c = 768
+            content = torch.randn((I, c), device=dev, generator=gen)
+            bound = (6.0 / (d + c + d)) ** 0.5                      # xavier_uniform of Linear(d+c, d)
+            W = torch.empty((d, d + c), device=dev).uniform_(-bound, bound, generator=gen)
+            bb = torch.empty((d,), device=dev).uniform_(-(d + c) ** -0.5, (d + c) ** -0.5, generator=gen)
+            fusion = dict(content=content, weight=W, bias=bb)
+        eng = LightGCNEngine(csr, U, I, B, K, table, batch_size=BS, fusion=fusion)
 
     tu_h, ti_h = tu.cpu(), ti.cpu()
     nb = args.steps + args.warmup
@@ -343,7 +351,7 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": args.workload, "num_users": U, "num_items": I, "nodes": N,
+            "config": {"workload": args.workload + ("+fusion768" if args.fusion else ""), "num_users": U, "num_items": I, "nodes": N,
                        "nnz": csr.nnz, "d": d, "layers": K, "batch": BS,
                        "steps_per_epoch": steps_per_epoch,
                        "parallelism": "single" if world == 1 else f"{args.parallelism}-sharded x{world}",
@@ -369,6 +377,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="amazon", choices=sorted(CPU_SAMPLE))
+    ap.add_argument("--fusion", action="store_true",
+                    help="LightGCN_Fusion: 768-d side embeddings projected and merged into the item "
+                         "rows of layer 0 (BASELINE.json configs[3]); single GPU")
     ap.add_argument("--eval-users", type=int, default=18944)
     ap.add_argument("--parallelism", default="feature", choices=["feature", "row"],
                     help="multi-GPU partitioning: feature columns (no propagation collectives) or "

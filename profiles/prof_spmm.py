@@ -17,6 +17,8 @@ mode = sys.argv[2] if len(sys.argv) > 2 else "plain"
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 dev = torch.device("cuda:0")
 U, I, B, total, d, K = synth.SHAPES[workload]
+if len(sys.argv) > 4:
+    d = int(sys.argv[4])
 inter = synth.generate_device(workload, dev, seed=0)
 tu, ti, _, _ = synth.split_validation_device(inter)
 g = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev)
