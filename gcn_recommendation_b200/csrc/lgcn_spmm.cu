@@ -36,11 +36,14 @@ constexpr int kThreads = kWarps * 32;
 template <int D, int RSEL>
 struct ChunkCfg {
     using G = RowGeom<D>;
-    static constexpr int RMAX = (2048 / D) < 4 ? 4 : (2048 / D);
-    static constexpr int RBIG = G::LANES < RMAX ? G::LANES : RMAX;
-    // rows per worker chunk: RSEL == 0 -> large chunks (big graphs: amortise the per-chunk
-    // pointer loads), RSEL == 1 -> 4-row chunks (small graphs: more workers, shorter chains)
+    // rows per worker chunk: RSEL == 0 -> 16 rows (8 at d=256; big graphs: amortise the
+    // per-chunk pointer loads), RSEL == 1 -> 4-row chunks (small graphs: more workers, shorter
+    // chains).  A lane keeps RPL = R / LANES row ends in registers (narrow tables have 4 or 8
+    // lanes per worker, e.g. the d/8 = 16 column slice of an 8-way feature-sharded table).
+    // (R > LANES, i.e. several row ends per lane, measured SLOWER at d=16/32: 2.34 vs 1.78 ms)
+    static constexpr int RBIG = D > 128 ? 8 : (G::LANES < 16 ? G::LANES : 16);
     static constexpr int R = RSEL == 0 ? RBIG : 4;
+    static constexpr int RPL = (R + G::LANES - 1) / G::LANES;
     static constexpr int WORKERS = kWarps * G::GROUPS;                // workers per CTA
     static constexpr int ROWS_PER_CTA = WORKERS * R;
     static constexpr int UMAX = G::VEC > 1 ? 4 : 8;                   // gathers per batch
@@ -209,19 +212,26 @@ __global__ void __launch_bounds__(kThreads, LGCN_SPMM_MINBLOCKS) spmm_chunk_kern
     const int64_t left = a.n_rows - r0;
     const int nvr = left <= 0 ? 0 : (left < C::R ? (int)left : C::R);
 
-    unsigned rb = 0, re = 0;
-    if (sub < nvr) {
-        rb = __ldg(a.rowptr + r0 + sub);
-        re = __ldg(a.rowptr + r0 + sub + 1);
+    // row ends: lane `sub` keeps the ends of rows sub, sub+LANES, ... (INT_MAX = never passed)
+    int my_end[C::RPL];
+    unsigned long_bits = 0;
+#pragma unroll
+    for (int i = 0; i < C::RPL; ++i) {
+        const int rr = i * G::LANES + sub;
+        unsigned rb = 0, re = 0x7fffffffu;
+        if (rr < nvr) {
+            rb = __ldg(a.rowptr + r0 + rr);
+            re = __ldg(a.rowptr + r0 + rr + 1) & 0x7fffffffu;
+        }
+        my_end[i] = (int)re;
+        const unsigned lb = (__ballot_sync(0xffffffffu, (rb >> 31) != 0) >> gshift) & gbits;
+        long_bits |= lb << (i * G::LANES);
     }
-    const bool my_long = (rb >> 31) != 0;
-    const int my_beg = (int)(rb & 0x7fffffffu);
-    int my_end = (int)(re & 0x7fffffffu);
-    int chunk_beg = __shfl_sync(0xffffffffu, my_beg, 0, G::LANES);
-    int chunk_end = __shfl_sync(0xffffffffu, my_end, nvr > 0 ? nvr - 1 : 0, G::LANES);
-    if (nvr == 0) chunk_beg = chunk_end = 0;
-    if (sub >= nvr) my_end = INT_MAX;                    // sentinel: never passed
-    const unsigned long_bits = (__ballot_sync(0xffffffffu, my_long) >> gshift) & gbits;
+    int chunk_beg = 0, chunk_end = 0;
+    if (nvr > 0) {
+        chunk_beg = (int)(__ldg(a.rowptr + r0) & 0x7fffffffu);
+        chunk_end = (int)(__ldg(a.rowptr + r0 + nvr) & 0x7fffffffu);
+    }
 
     const int n_e = chunk_end - chunk_beg;
     int max_n = n_e;
@@ -271,9 +281,11 @@ __global__ void __launch_bounds__(kThreads, LGCN_SPMM_MINBLOCKS) spmm_chunk_kern
                 const float wj = __int_as_float(__shfl_sync(0xffffffffu, cv.y, j + u, G::LANES));
                 const int e = chunk_beg + t + j + u;
                 // rows of this chunk that end at or before e (one ballot, no per-row pointer chase)
-                const unsigned passed = (__ballot_sync(0xffffffffu, my_end <= e) >> gshift) & gbits;
+                int row = 0;
+#pragma unroll
+                for (int i = 0; i < C::RPL; ++i)
+                    row += __popc((__ballot_sync(0xffffffffu, my_end[i] <= e) >> gshift) & gbits);
                 if (j + u < cnt) {
-                    const int row = __popc(passed);
                     if (row != cur) {                     // flush the finished row, zero the empty ones
 #pragma unroll
                         for (int v = 0; v < G::VEC; ++v) {
