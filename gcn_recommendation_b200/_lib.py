@@ -18,7 +18,7 @@ c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctyp
 SPMM_PLAIN, SPMM_ADD, SPMM_MEAN, SPMM_ADAM = 0, 1, 2, 3
 SPMM_F_STREAM_HINTS = 1
 BPR_GP_INCLUDES_GF, BPR_NO_GRAD = 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class SpmmArgs(ctypes.Structure):
@@ -31,7 +31,7 @@ class SpmmArgs(ctypes.Structure):
         ("long_seg_ptr", c_vp), ("seg_len", c_i32), ("n_seg", c_i32), ("seg_ws", c_vp),
         ("addend2", c_vp), ("p", c_vp), ("m", c_vp), ("v", c_vp), ("adam_scalars", c_vp),
         ("beta1", c_f32), ("beta2", c_f32), ("eps", c_f32), ("g_out", c_vp),
-        ("flags", c_i32),
+        ("flags", c_i32), ("x_rowflag", c_vp), ("addend_rowflag", c_vp), ("zero_row", c_vp),
     ]
 
 
@@ -43,11 +43,11 @@ _SIGNATURES = {
     "lgcn_spmm": (ctypes.c_int, [ctypes.POINTER(SpmmArgs), c_vp]),
     "lgcn_sizeof_spmm_args": (ctypes.c_size_t, []),
     "lgcn_bpr_fused": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_f32,
-                                      c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+                                      c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "lgcn_bpr_partial": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp]),
     "lgcn_bpr_apply": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_f32,
-                                      c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "lgcn_zero_rows": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_vp]),
+                                      c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "lgcn_zero_rows": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_vp]),
     "lgcn_adam_tick": (ctypes.c_int, [c_vp, c_vp, c_f32, c_f32, c_f32, c_vp]),
     "lgcn_adam": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_f32, c_f32, c_f32,
                                  c_vp]),
@@ -102,7 +102,8 @@ def check(rc):
         raise LgcnError(f"lgcn call failed ({rc}): {msg}")
 
 
-_DT = {"f32": torch.float32, "i32": torch.int32, "i64": torch.int64, "f64": torch.float64}
+_DT = {"f32": torch.float32, "i32": torch.int32, "i64": torch.int64, "f64": torch.float64,
+       "u8": torch.uint8}
 
 
 def ptr(t, dt="f32", allow_none=False):

@@ -28,7 +28,7 @@ bpr_kernel(const float *__restrict__ F, const float *__restrict__ P,
            const int64_t *__restrict__ users, const int64_t *__restrict__ pos,
            const int64_t *__restrict__ neg, int64_t bs, int64_t item_offset, float lam,
            float grad_scale, int flags, float *__restrict__ dots, float *__restrict__ sample_ws,
-           float *__restrict__ gF, float *__restrict__ gP) {
+           float *__restrict__ gF, float *__restrict__ gP, uint8_t *__restrict__ rowflag) {
     using G = RowGeom<D>;
     const int lane = threadIdx.x & 31;
     const int64_t s = (int64_t)blockIdx.x * (kBprThreads / 32) + (threadIdx.x >> 5);
@@ -80,6 +80,7 @@ bpr_kernel(const float *__restrict__ F, const float *__restrict__ P,
     // d/dx -log(sigmoid(x)+1e-8) = -sg(1-sg)/(sg+1e-8); mean over the batch
     const float coef = -sg * (1.0f - sg) / (sg + 1e-8f) * invB * grad_scale;
     const float c2 = 2.0f * lam * invB;            // main.py:394-398 (no 1/2)
+    if (rowflag && lane == 0) { rowflag[ru] = 1; rowflag[rp] = 1; rowflag[rn] = 1; }
     if (!act) return;
     const bool both = (flags & LGCN_BPR_GP_INCLUDES_GF) != 0;
 #pragma unroll
@@ -135,14 +136,15 @@ __global__ void __launch_bounds__(1024) bpr_reduce_kernel(const float *__restric
 
 template <int D>
 __global__ void __launch_bounds__(kBprThreads)
-zero_rows_kernel(float *__restrict__ t0, float *__restrict__ t1, const int64_t *__restrict__ users,
-                 const int64_t *__restrict__ pos, const int64_t *__restrict__ neg, int64_t bs,
-                 int64_t item_offset) {
+zero_rows_kernel(float *__restrict__ t0, float *__restrict__ t1, uint8_t *__restrict__ rowflag,
+                 const int64_t *__restrict__ users, const int64_t *__restrict__ pos,
+                 const int64_t *__restrict__ neg, int64_t bs, int64_t item_offset) {
     using G = RowGeom<D>;
     const int lane = threadIdx.x & 31;
     const int64_t s = (int64_t)blockIdx.x * (kBprThreads / 32) + (threadIdx.x >> 5);
     if (s >= bs || lane >= G::LANES) return;
     const int64_t rows[3] = {users[s], item_offset + pos[s], item_offset + neg[s]};
+    if (rowflag && lane == 0) { rowflag[rows[0]] = 0; rowflag[rows[1]] = 0; rowflag[rows[2]] = 0; }
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 3; ++k)
@@ -194,14 +196,14 @@ template <int PHASE>
 static int bpr_launch(const float *F, const float *P, const int64_t *users, const int64_t *pos,
                       const int64_t *neg, int64_t bs, int32_t d, int64_t item_offset, float lam,
                       float grad_scale, int32_t flags, float *dots, float *sample_ws, float *gF,
-                      float *gP, cudaStream_t st) {
+                      float *gP, uint8_t *rowflag, cudaStream_t st) {
     using namespace lgcn;
     const unsigned grid = (unsigned)((bs + kBprThreads / 32 - 1) / (kBprThreads / 32));
 #define LGCN_BPR_CASE(DD)                                                                          \
     case DD:                                                                                       \
         bpr_kernel<DD, PHASE><<<grid, kBprThreads, 0, st>>>(F, P, users, pos, neg, bs, item_offset, \
                                                             lam, grad_scale, flags, dots, sample_ws, \
-                                                            gF, gP);                               \
+                                                            gF, gP, rowflag);                      \
         break;
     switch (d) {
         LGCN_BPR_CASE(16) LGCN_BPR_CASE(32) LGCN_BPR_CASE(64) LGCN_BPR_CASE(128) LGCN_BPR_CASE(256)
@@ -216,13 +218,13 @@ extern "C" int lgcn_bpr_fused(const float *F, const float *P, const int64_t *use
                               const int64_t *pos, const int64_t *neg, int64_t bs, int32_t d,
                               int64_t item_offset, float lam, float grad_scale, int32_t flags,
                               float *sample_ws, float *loss_out, float *gF, float *gP,
-                              lgcn_stream_t stream) {
+                              uint8_t *rowflag, lgcn_stream_t stream) {
     using namespace lgcn;
     if (!dim_supported(d)) return LGCN_E_BAD_DIM;
     if (bs <= 0 || !F || !P || !users || !pos || !neg || !sample_ws || !loss_out) return LGCN_E_BAD_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int rc = bpr_launch<0>(F, P, users, pos, neg, bs, d, item_offset, lam, grad_scale, flags, nullptr,
-                           sample_ws, gF, gP, st);
+                           sample_ws, gF, gP, rowflag, st);
     if (rc) return rc;
     bpr_reduce_kernel<<<1, 1024, 0, st>>>(sample_ws, bs, lam, loss_out);
     LGCN_LAUNCH_CHECK();
@@ -236,30 +238,30 @@ extern "C" int lgcn_bpr_partial(const float *F, const float *P, const int64_t *u
     if (!dim_supported(d)) return LGCN_E_BAD_DIM;
     if (bs <= 0 || !F || !P || !users || !pos || !neg || !dots) return LGCN_E_BAD_ARG;
     return bpr_launch<1>(F, P, users, pos, neg, bs, d, item_offset, 0.f, 0.f, 0, dots, nullptr,
-                         nullptr, nullptr, reinterpret_cast<cudaStream_t>(stream));
+                         nullptr, nullptr, nullptr, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int lgcn_bpr_apply(const float *F, const float *P, const int64_t *users,
                               const int64_t *pos, const int64_t *neg, int64_t bs, int32_t d,
                               int64_t item_offset, float lam, float grad_scale, int32_t flags,
                               const float *dots, float *sample_ws, float *loss_out, float *gF,
-                              float *gP, lgcn_stream_t stream) {
+                              float *gP, uint8_t *rowflag, lgcn_stream_t stream) {
     using namespace lgcn;
     if (!dim_supported(d)) return LGCN_E_BAD_DIM;
     if (bs <= 0 || !F || !P || !users || !pos || !neg || !dots || !sample_ws || !loss_out)
         return LGCN_E_BAD_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int rc = bpr_launch<2>(F, P, users, pos, neg, bs, d, item_offset, lam, grad_scale, flags,
-                           const_cast<float *>(dots), sample_ws, gF, gP, st);
+                           const_cast<float *>(dots), sample_ws, gF, gP, rowflag, st);
     if (rc) return rc;
     bpr_reduce_kernel<<<1, 1024, 0, st>>>(sample_ws, bs, lam, loss_out);
     LGCN_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int lgcn_zero_rows(float *t0, float *t1, const int64_t *users, const int64_t *pos,
-                              const int64_t *neg, int64_t bs, int32_t d, int64_t item_offset,
-                              lgcn_stream_t stream) {
+extern "C" int lgcn_zero_rows(float *t0, float *t1, uint8_t *rowflag, const int64_t *users,
+                              const int64_t *pos, const int64_t *neg, int64_t bs, int32_t d,
+                              int64_t item_offset, lgcn_stream_t stream) {
     using namespace lgcn;
     if (!dim_supported(d)) return LGCN_E_BAD_DIM;
     if (bs <= 0 || !users || !pos || !neg) return LGCN_E_BAD_ARG;
@@ -267,7 +269,7 @@ extern "C" int lgcn_zero_rows(float *t0, float *t1, const int64_t *users, const 
     const unsigned grid = (unsigned)((bs + kBprThreads / 32 - 1) / (kBprThreads / 32));
 #define LGCN_ZR_CASE(DD)                                                                          \
     case DD:                                                                                      \
-        zero_rows_kernel<DD><<<grid, kBprThreads, 0, st>>>(t0, t1, users, pos, neg, bs,           \
+        zero_rows_kernel<DD><<<grid, kBprThreads, 0, st>>>(t0, t1, rowflag, users, pos, neg, bs,  \
                                                            item_offset);                          \
         break;
     switch (d) { LGCN_ZR_CASE(16) LGCN_ZR_CASE(32) LGCN_ZR_CASE(64) LGCN_ZR_CASE(128) LGCN_ZR_CASE(256) }

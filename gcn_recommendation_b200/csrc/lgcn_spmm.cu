@@ -137,7 +137,13 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
             } else if (MODE == LGCN_SPMM_ADD) {
                 float4 t[B];
 #pragma unroll
-                for (int i = 0; i < B; ++i) if (on[i]) t[i] = ld_s<HINT>(a.addend + off[i], pol);
+                for (int i = 0; i < B; ++i)
+                    if (on[i]) {
+                        // all-zero addend rows (no gradient landed there) are read from the
+                        // cache-resident zero row instead of HBM
+                        const bool nz = !a.addend_rowflag || __ldg(a.addend_rowflag + r0 + rb + i) != 0;
+                        t[i] = ld_s<HINT>(nz ? a.addend + off[i] : a.zero_row + coff, pol);
+                    }
 #pragma unroll
                 for (int i = 0; i < B; ++i)
                     if (on[i]) {
@@ -169,8 +175,9 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
 #pragma unroll
                 for (int i = 0; i < B; ++i)
                     if (on[i]) {
-                        if (a.addend) g[i] = ld_s<HINT>(a.addend + off[i], pol);
-                        if (a.addend2) g2[i] = ld_s<HINT>(a.addend2 + off[i], pol);
+                        const bool nz = !a.addend_rowflag || __ldg(a.addend_rowflag + r0 + rb + i) != 0;
+                        if (a.addend) g[i] = ld_s<HINT>(nz ? a.addend + off[i] : a.zero_row + coff, pol);
+                        if (a.addend2) g2[i] = ld_s<HINT>(nz ? a.addend2 + off[i] : a.zero_row + coff, pol);
                         p[i] = ld_s<HINT>(a.p + off[i], pol);
                         m[i] = ld_s<HINT>(a.m + off[i], pol);
                         vv[i] = ld_s<HINT>(a.v + off[i], pol);
@@ -193,7 +200,7 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
 }
 
 // ---- main kernel: one worker per chunk of R rows ---------------------------------------------
-template <int D, int MODE, int RSEL, bool HINT>
+template <int D, int MODE, int RSEL, bool HINT, bool XF>
 __global__ void __launch_bounds__(kThreads, LGCN_SPMM_MINBLOCKS) spmm_chunk_kernel(const lgcn_spmm_args a) {
     using G = RowGeom<D>;
     using C = ChunkCfg<D, RSEL>;
@@ -270,9 +277,11 @@ __global__ void __launch_bounds__(kThreads, LGCN_SPMM_MINBLOCKS) spmm_chunk_kern
             for (int u = 0; u < U; ++u) {
                 // unconditional: slots past the end carry col 0 (a valid, cache-resident row).  A
                 // predicated 128-bit load makes ptxas stage through 4 temporaries and serialises
-                // the batch (ncu: stalls on the predicated MOVs).
+                // the batch (ncu: stalls on the predicated MOVs).  Rows flagged all-zero (XF: the
+                // sparse g' of the first backward hop) are redirected to the zero row likewise.
                 const int cj = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
                 const float *src = a.x + (size_t)cj * D + sub * 4;
+                if (XF) src = __ldg(a.x_rowflag + cj) ? src : a.zero_row + sub * 4;
 #pragma unroll
                 for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
             }
@@ -358,11 +367,9 @@ __global__ void __launch_bounds__(kThreads) spmm_long_seg_kernel(const lgcn_spmm
                 for (int v = 0; v < G::VEC; ++v) x[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                // unconditional: slots past the end carry col 0 (a valid, cache-resident row).  A
-                // predicated 128-bit load makes ptxas stage through 4 temporaries and serialises
-                // the batch (ncu: stalls on the predicated MOVs).
                 const int cj = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
                 const float *src = a.x + (size_t)cj * D + sub * 4;
+                if (a.x_rowflag) src = __ldg(a.x_rowflag + cj) ? src : a.zero_row + sub * 4;
 #pragma unroll
                 for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
             }
@@ -420,19 +427,19 @@ __global__ void __launch_bounds__(kThreads) spmm_long_combine_kernel(const lgcn_
     epilogue_row<D, MODE>(a, __ldg(a.long_row_ids + i), acc);
 }
 
-template <int D, int MODE, int RSEL, bool HINT>
+template <int D, int MODE, int RSEL, bool HINT, bool XF>
 static int launch_chunks(const lgcn_spmm_args &a, cudaStream_t st) {
     using C = ChunkCfg<D, RSEL>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(spmm_chunk_kernel<D, MODE, RSEL, HINT>,
+        cudaError_t e = cudaFuncSetAttribute(spmm_chunk_kernel<D, MODE, RSEL, HINT, XF>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
     const int64_t gb = (a.n_rows + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
     if (gb > 0x7fffffffLL) return LGCN_E_TOO_LARGE;
-    spmm_chunk_kernel<D, MODE, RSEL, HINT><<<(unsigned)gb, kThreads, C::SMEM, st>>>(a);
+    spmm_chunk_kernel<D, MODE, RSEL, HINT, XF><<<(unsigned)gb, kThreads, C::SMEM, st>>>(a);
     LGCN_LAUNCH_CHECK();
     return 0;
 }
@@ -452,9 +459,14 @@ static int launch_mode(const lgcn_spmm_args &a, cudaStream_t st) {
         const bool small = big_workers < (int64_t)kNumSMs * 32 * G::GROUPS;
         const bool hint = (a.flags & LGCN_SPMM_F_STREAM_HINTS) != 0;
         int rc;
-        if (small) rc = launch_chunks<D, MODE, 1, false>(a, st);
-        else if (hint) rc = launch_chunks<D, MODE, 0, true>(a, st);
-        else rc = launch_chunks<D, MODE, 0, false>(a, st);
+        const bool xf = MODE == LGCN_SPMM_ADD && a.x_rowflag != nullptr;
+        if (xf) {               // sparse-input hop (first Horner hop): flagged gathers
+            if (small) rc = launch_chunks<D, LGCN_SPMM_ADD, 1, false, true>(a, st);
+            else if (hint) rc = launch_chunks<D, LGCN_SPMM_ADD, 0, true, true>(a, st);
+            else rc = launch_chunks<D, LGCN_SPMM_ADD, 0, false, true>(a, st);
+        } else if (small) rc = launch_chunks<D, MODE, 1, false, false>(a, st);
+        else if (hint) rc = launch_chunks<D, MODE, 0, true, false>(a, st);
+        else rc = launch_chunks<D, MODE, 0, false, false>(a, st);
         if (rc) return rc;
     }
     if (a.n_long > 0) {
@@ -499,6 +511,8 @@ extern "C" int lgcn_spmm(const lgcn_spmm_args *args, lgcn_stream_t stream) {
         default: return LGCN_E_BAD_ARG;
     }
     if (a.n_long < 0) return LGCN_E_BAD_ARG;
+    if ((a.x_rowflag || a.addend_rowflag) && !a.zero_row) return LGCN_E_BAD_ARG;
+    if (a.x_rowflag && a.mode != LGCN_SPMM_ADD) return LGCN_E_BAD_ARG;
     if (a.n_long > 0 && (!a.long_row_ids || !a.long_rowptr || !a.long_colval || !a.long_seg_ptr ||
                          !a.seg_ws || a.seg_len <= 0 || a.n_seg <= 0))
         return LGCN_E_BAD_ARG;

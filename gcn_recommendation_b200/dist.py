@@ -54,7 +54,8 @@ class FeatureShardedEngine(LightGCNEngine):
         self._allreduce(self.dots)                     # the only collective of the step
         ops.bpr_apply(F, self.P, u, p, n, self.U, self.lam, self.dots,
                       grad_scale=1.0 / (self.K + 1), gF=self.G1, gP=self.G2,
-                      gp_includes_gf=gp_includes_gf, sample_ws=self.sample_ws, loss_out=self.loss)
+                      gp_includes_gf=gp_includes_gf, sample_ws=self.sample_ws, loss_out=self.loss,
+                      rowflag=self.rowflag)
 
     def gather_final_table(self):
         """All-gather the propagated table over the feature dimension -> [N, d] on every rank."""

@@ -87,6 +87,10 @@ class LightGCNEngine:
         self.work = [new() for _ in range(max(self.K - 1, 2 if self.K > 1 else 0))]
         self.G1 = torch.zeros_like(self.P)          # g/(K+1): addend of every Horner hop
         self.G2 = torch.zeros_like(self.P)          # regulariser grad (+ g/(K+1) w/o fusion)
+        # 1 = row received a gradient this step (G1/G2 are zero elsewhere): lets the backward
+        # hops skip the gathers / addend reads of all-zero rows
+        self.rowflag = torch.zeros(self.N, dtype=torch.uint8, device=self.dev)
+        self.zero_row = torch.zeros(256, dtype=torch.float32, device=self.dev)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.adam_scalars = torch.zeros(2, dtype=torch.float32, device=self.dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
@@ -152,7 +156,8 @@ class LightGCNEngine:
         into G2 for the staged batch (reference ``main.py:496-497,515-525``)."""
         ops.bpr_fused(F, self.P, self.b_users, self.b_pos, self.b_neg, self.U, self.lam,
                       grad_scale=1.0 / (self.K + 1), gF=self.G1, gP=self.G2,
-                      gp_includes_gf=gp_includes_gf, sample_ws=self.sample_ws, loss_out=self.loss)
+                      gp_includes_gf=gp_includes_gf, sample_ws=self.sample_ws, loss_out=self.loss,
+                      rowflag=self.rowflag)
 
     def _step_body(self):
         g, K, U, I = self.g, self.K, self.U, self.I
@@ -163,11 +168,14 @@ class LightGCNEngine:
         ops.adam_tick(self.step_dev, self.adam_scalars, self.lr, self.betas)
         acc = self.G1
         hops = K - 1 if nofus else K
+        rf, zr = self.rowflag, self.zero_row
         for k in range(hops):
-            acc = ops.spmm(g, acc, out=self.work[k % 2] if K > 1 else self.F, addend=self.G1)
+            # hop 0 gathers g' itself (<= 3*batch non-zero rows): flagged gathers
+            acc = ops.spmm(g, acc, out=self.work[k % 2] if K > 1 else self.F, addend=self.G1,
+                           x_rowflag=rf if k == 0 else None, addend_rowflag=rf, zero_row=zr)
         if nofus:
             ops.spmm_adam(g, acc, self.P, self.m, self.v, self.adam_scalars, addend=self.G2,
-                          betas=self.betas, eps=self.eps)
+                          betas=self.betas, eps=self.eps, addend_rowflag=rf, zero_row=zr)
         else:
             f = self.fusion
             f["gW"].zero_()
@@ -184,7 +192,7 @@ class LightGCNEngine:
                          g1=self.G2[U + I:], **kw)
             ops.adam(f["W"], f["gW"], f["mW"], f["vW"], sc, **kw)
             ops.adam(f["b"], f["gb"], f["mb"], f["vb"], sc, **kw)
-        ops.zero_rows(self.G1, self.G2, u, p, n, U)
+        ops.zero_rows(self.G1, self.G2, u, p, n, U, rowflag=self.rowflag)
 
     # ---- public --------------------------------------------------------------------------
     def capture(self):

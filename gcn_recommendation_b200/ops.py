@@ -57,7 +57,8 @@ def _check_table(t, rows, d, name):
         raise _lib.LgcnError(f"{name}: expected at least [{rows},{d}], got {tuple(t.shape)}")
 
 
-def spmm(g, x, out=None, addend=None, mean_layers=None):
+def spmm(g, x, out=None, addend=None, mean_layers=None, x_rowflag=None, addend_rowflag=None,
+         zero_row=None):
     """out = A_hat x  (+ addend)  |  mean over [*mean_layers, A_hat x] (reference
     ``models/lightgcn.py:45,54``).  ``g``: :class:`graph.NormAdjCSR`; ``x`` [n_cols, d]."""
     d = x.shape[1]
@@ -79,6 +80,10 @@ def spmm(g, x, out=None, addend=None, mean_layers=None):
         _check_table(addend, g.n_rows, d, "addend")
         a = _spmm_args(g, x, SPMM_ADD, d)
         a.addend = ptr(addend)
+        if x_rowflag is not None or addend_rowflag is not None:
+            a.x_rowflag = ptr(x_rowflag, "u8", allow_none=True)
+            a.addend_rowflag = ptr(addend_rowflag, "u8", allow_none=True)
+            a.zero_row = ptr(zero_row)
     else:
         a = _spmm_args(g, x, SPMM_PLAIN, d)
     a.y = ptr(out)
@@ -87,7 +92,7 @@ def spmm(g, x, out=None, addend=None, mean_layers=None):
 
 
 def spmm_adam(g, x, p, m, v, adam_scalars, addend=None, addend2=None, betas=(0.9, 0.999),
-              eps=1e-8, g_out=None):
+              eps=1e-8, g_out=None, addend_rowflag=None, zero_row=None):
     """Last backward hop fused with Adam: grad = addend + A_hat x + addend2; Adam(p, m, v, grad)
     (reference ``main.py:525-526``)."""
     d = x.shape[1]
@@ -100,6 +105,9 @@ def spmm_adam(g, x, p, m, v, adam_scalars, addend=None, addend2=None, betas=(0.9
     a.adam_scalars = ptr(adam_scalars)
     a.beta1, a.beta2, a.eps = betas[0], betas[1], eps
     a.g_out = ptr(g_out, allow_none=True)
+    if addend_rowflag is not None:
+        a.addend_rowflag = ptr(addend_rowflag, "u8")
+        a.zero_row = ptr(zero_row)
     _launch_spmm(a, g, x.device, "adam")
 
 
@@ -128,7 +136,7 @@ def propagate_backward(g, grad_f, n_layers, work=None):
 
 
 def bpr_fused(F, P, users, pos, neg, num_users, lam, grad_scale=1.0, gF=None, gP=None,
-              gp_includes_gf=False, sample_ws=None, loss_out=None):
+              gp_includes_gf=False, sample_ws=None, loss_out=None, rowflag=None):
     """Fused gather + BPR + L2 + scatter-add (reference ``main.py:366-402,496-497``)."""
     bs = users.numel()
     d = F.shape[1]
@@ -146,7 +154,8 @@ def bpr_fused(F, P, users, pos, neg, num_users, lam, grad_scale=1.0, gF=None, gP
     check(_lib.load().lgcn_bpr_fused(ptr(F), ptr(P), ptr(users, "i64"), ptr(pos, "i64"),
                                      ptr(neg, "i64"), bs, d, num_users, lam, grad_scale, flags,
                                      ptr(sample_ws), ptr(loss_out), ptr(gF, allow_none=True),
-                                     ptr(gP, allow_none=True), stream_ptr(dev)))
+                                     ptr(gP, allow_none=True), ptr(rowflag, "u8", allow_none=True),
+                                     stream_ptr(dev)))
     return loss_out
 
 
@@ -160,7 +169,7 @@ def bpr_partial(F, P, users, pos, neg, num_users, dots):
 
 
 def bpr_apply(F, P, users, pos, neg, num_users, lam, dots, grad_scale=1.0, gF=None, gP=None,
-              gp_includes_gf=False, sample_ws=None, loss_out=None):
+              gp_includes_gf=False, sample_ws=None, loss_out=None, rowflag=None):
     """Feature-sharded step, phase 2: loss from the rank-summed dots, scatter local columns."""
     bs = users.numel()
     dev = F.device
@@ -178,14 +187,15 @@ def bpr_apply(F, P, users, pos, neg, num_users, lam, dots, grad_scale=1.0, gF=No
                                      ptr(neg, "i64"), bs, F.shape[1], num_users, lam, grad_scale,
                                      flags, ptr(dots), ptr(sample_ws), ptr(loss_out),
                                      ptr(gF, allow_none=True), ptr(gP, allow_none=True),
-                                     stream_ptr(dev)))
+                                     ptr(rowflag, "u8", allow_none=True), stream_ptr(dev)))
     return loss_out
 
 
-def zero_rows(t0, t1, users, pos, neg, num_users):
+def zero_rows(t0, t1, users, pos, neg, num_users, rowflag=None):
     d = t0.shape[1]
     COUNTERS["launches"] += 1
-    check(_lib.load().lgcn_zero_rows(ptr(t0), ptr(t1, allow_none=True), ptr(users, "i64"),
+    check(_lib.load().lgcn_zero_rows(ptr(t0), ptr(t1, allow_none=True),
+                                     ptr(rowflag, "u8", allow_none=True), ptr(users, "i64"),
                                      ptr(pos, "i64"), ptr(neg, "i64"), users.numel(), d, num_users,
                                      stream_ptr(t0.device)))
 

@@ -33,7 +33,7 @@ typedef struct CUstream_st *lgcn_stream_t; /* == cudaStream_t */
 #define LGCN_API
 #endif
 
-#define LGCN_ABI_VERSION 2
+#define LGCN_ABI_VERSION 3
 
 #define LGCN_E_BAD_DIM   (-1) /* embedding dim not supported              */
 #define LGCN_E_BAD_ARG   (-2) /* null pointer / negative size / bad mode  */
@@ -112,6 +112,15 @@ typedef struct lgcn_spmm_args {
     float          beta1, beta2, eps;
     float         *g_out;       /* ADAM: optional [n_rows,d] copy of g (NULL = none)      */
     int32_t        flags;       /* LGCN_SPMM_F_*                                          */
+    /* Sparse-gradient shortcuts of the backward pass (all optional, NULL = dense):
+     * x_rowflag[c] == 0 means row c of x is all zero, so its gather is skipped (mode ADD only;
+     * the first Horner hop reads g', which has at most 3*batch non-zero rows);
+     * addend_rowflag[r] == 0 means row r of addend (and addend2) is all zero and is not read.
+     * zero_row: a zero-filled device buffer of >= d floats the skipped loads are redirected to
+     * (required when either flag array is given). */
+    const uint8_t *x_rowflag;
+    const uint8_t *addend_rowflag;
+    const float   *zero_row;
 } lgcn_spmm_args;
 
 /* tables do not fit L2: stream entries / outputs / epilogue operands with L2 evict_first so
@@ -139,6 +148,8 @@ LGCN_API size_t lgcn_sizeof_spmm_args(void);
  *           (+ the gF contribution too when LGCN_BPR_GP_INCLUDES_GF is set)
  * F: [N,d] propagated table; P: [N,d] layer-0 id table (the 4th/5th forward outputs);
  * io = item_offset = num_users.  sample_ws: [2*bs] floats of scratch.  loss_out: [1].
+ * rowflag (optional, [N] bytes): set to 1 for every row that received a gradient, so that the
+ * backward SpMM hops can skip the all-zero rows of gF / gP (see lgcn_spmm_args.x_rowflag).
  * ------------------------------------------------------------------------------------- */
 #define LGCN_BPR_GP_INCLUDES_GF 1
 #define LGCN_BPR_NO_GRAD        2 /* loss only */
@@ -146,7 +157,7 @@ LGCN_API size_t lgcn_sizeof_spmm_args(void);
 LGCN_API int lgcn_bpr_fused(const float *F, const float *P, const int64_t *users, const int64_t *pos,
                    const int64_t *neg, int64_t bs, int32_t d, int64_t item_offset, float lam,
                    float grad_scale, int32_t flags, float *sample_ws, float *loss_out,
-                   float *gF, float *gP, lgcn_stream_t stream);
+                   float *gF, float *gP, uint8_t *rowflag, lgcn_stream_t stream);
 
 /* Feature-sharded tables (every rank owns d/P columns of every row): the step is split around
  * one small all-reduce.  lgcn_bpr_partial writes this rank's partial sums dots[0:bs]=<u,p>,
@@ -158,12 +169,12 @@ LGCN_API int lgcn_bpr_partial(const float *F, const float *P, const int64_t *use
 LGCN_API int lgcn_bpr_apply(const float *F, const float *P, const int64_t *users, const int64_t *pos,
                    const int64_t *neg, int64_t bs, int32_t d, int64_t item_offset, float lam,
                    float grad_scale, int32_t flags, const float *dots, float *sample_ws,
-                   float *loss_out, float *gF, float *gP, lgcn_stream_t stream);
+                   float *loss_out, float *gF, float *gP, uint8_t *rowflag, lgcn_stream_t stream);
 
 /* zero the rows {u_s, io+p_s, io+n_s} of up to two [N,d] tables (undo of the scatter) */
-LGCN_API int lgcn_zero_rows(float *t0, float *t1, const int64_t *users, const int64_t *pos,
-                   const int64_t *neg, int64_t bs, int32_t d, int64_t item_offset,
-                   lgcn_stream_t stream);
+LGCN_API int lgcn_zero_rows(float *t0, float *t1, uint8_t *rowflag, const int64_t *users,
+                   const int64_t *pos, const int64_t *neg, int64_t bs, int32_t d,
+                   int64_t item_offset, lgcn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * a5  Dense Adam (torch.optim.Adam defaults, reference main.py:469,526).
