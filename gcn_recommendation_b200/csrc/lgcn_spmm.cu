@@ -36,14 +36,13 @@ constexpr int kThreads = kWarps * 32;
 template <int D, int RSEL>
 struct ChunkCfg {
     using G = RowGeom<D>;
-    // rows per worker chunk: RSEL == 0 -> 16 rows (8 at d=256; big graphs: amortise the
-    // per-chunk pointer loads), RSEL == 1 -> 4-row chunks (small graphs: more workers, shorter
-    // chains).  A lane keeps RPL = R / LANES row ends in registers (narrow tables have 4 or 8
-    // lanes per worker, e.g. the d/8 = 16 column slice of an 8-way feature-sharded table).
-    // (R > LANES, i.e. several row ends per lane, measured SLOWER at d=16/32: 2.34 vs 1.78 ms)
-    static constexpr int RBIG = D > 128 ? 8 : (G::LANES < 16 ? G::LANES : 16);
+    // rows per worker chunk: RSEL == 0 -> up to 16 rows (big graphs: amortise the per-chunk
+    // pointer loads), RSEL == 1 -> 4-row chunks (small graphs: more workers, shorter chains).
+    // One row end per lane (R <= LANES).  Several row ends per lane (R > LANES for narrow
+    // tables) was measured slower at d=16/32 and cost 8 registers at d=128.
+    static constexpr int RMAX = (2048 / D) < 4 ? 4 : (2048 / D);
+    static constexpr int RBIG = G::LANES < RMAX ? G::LANES : RMAX;
     static constexpr int R = RSEL == 0 ? RBIG : 4;
-    static constexpr int RPL = (R + G::LANES - 1) / G::LANES;
     static constexpr int WORKERS = kWarps * G::GROUPS;                // workers per CTA
     static constexpr int ROWS_PER_CTA = WORKERS * R;
     static constexpr int UMAX = G::VEC > 1 ? 4 : 8;                   // gathers per batch
@@ -109,7 +108,8 @@ __device__ __forceinline__ void epilogue_row(const lgcn_spmm_args &a, int64_t ro
 // ---- chunk epilogue: stream the staged rows, operand loads batched ahead of the math ------
 template <int D, int MODE, int RSEL, bool HINT>
 __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const float *stage,
-                                               int64_t r0, int nvr, unsigned long_bits, uint64_t pol) {
+                                               int64_t r0, int nvr, unsigned long_bits, uint64_t pol,
+                                               const unsigned (&rfw)[ChunkCfg<D, RSEL>::R / 4]) {
     using G = RowGeom<D>;
     using C = ChunkCfg<D, RSEL>;
     const int sub = (threadIdx.x & 31) % G::LANES;
@@ -141,7 +141,7 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
                     if (on[i]) {
                         // all-zero addend rows (no gradient landed there) are read from the
                         // cache-resident zero row instead of HBM
-                        const bool nz = !a.addend_rowflag || __ldg(a.addend_rowflag + r0 + rb + i) != 0;
+                        const bool nz = ((rfw[(rb + i) >> 2] >> (((rb + i) & 3) * 8)) & 0xffu) != 0;
                         t[i] = ld_s<HINT>(nz ? a.addend + off[i] : a.zero_row + coff, pol);
                     }
 #pragma unroll
@@ -175,7 +175,7 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
 #pragma unroll
                 for (int i = 0; i < B; ++i)
                     if (on[i]) {
-                        const bool nz = !a.addend_rowflag || __ldg(a.addend_rowflag + r0 + rb + i) != 0;
+                        const bool nz = ((rfw[(rb + i) >> 2] >> (((rb + i) & 3) * 8)) & 0xffu) != 0;
                         if (a.addend) g[i] = ld_s<HINT>(nz ? a.addend + off[i] : a.zero_row + coff, pol);
                         if (a.addend2) g2[i] = ld_s<HINT>(nz ? a.addend2 + off[i] : a.zero_row + coff, pol);
                         p[i] = ld_s<HINT>(a.p + off[i], pol);
@@ -201,7 +201,7 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
 
 // ---- main kernel: one worker per chunk of R rows ---------------------------------------------
 template <int D, int MODE, int RSEL, bool HINT, bool XF>
-__global__ void __launch_bounds__(kThreads, LGCN_SPMM_MINBLOCKS) spmm_chunk_kernel(const lgcn_spmm_args a) {
+__global__ void __launch_bounds__(kThreads, LGCN_SPMM_MINBLOCKS) spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
     using G = RowGeom<D>;
     using C = ChunkCfg<D, RSEL>;
     const uint64_t pol = HINT ? policy_evict_first() : 0ull;
@@ -219,26 +219,26 @@ __global__ void __launch_bounds__(kThreads, LGCN_SPMM_MINBLOCKS) spmm_chunk_kern
     const int64_t left = a.n_rows - r0;
     const int nvr = left <= 0 ? 0 : (left < C::R ? (int)left : C::R);
 
-    // row ends: lane `sub` keeps the ends of rows sub, sub+LANES, ... (INT_MAX = never passed)
-    int my_end[C::RPL];
-    unsigned long_bits = 0;
+    // "row received a gradient" flags of the chunk's addend rows (bytes r0 .. r0+R, the array is
+    // padded): fetched up front so that the epilogue has no dependent flag -> addend load chain
+    unsigned rfw[C::R / 4];
 #pragma unroll
-    for (int i = 0; i < C::RPL; ++i) {
-        const int rr = i * G::LANES + sub;
-        unsigned rb = 0, re = 0x7fffffffu;
-        if (rr < nvr) {
-            rb = __ldg(a.rowptr + r0 + rr);
-            re = __ldg(a.rowptr + r0 + rr + 1) & 0x7fffffffu;
-        }
-        my_end[i] = (int)re;
-        const unsigned lb = (__ballot_sync(0xffffffffu, (rb >> 31) != 0) >> gshift) & gbits;
-        long_bits |= lb << (i * G::LANES);
+    for (int i = 0; i < C::R / 4; ++i)
+        rfw[i] = ((MODE == LGCN_SPMM_ADD || MODE == LGCN_SPMM_ADAM) && a.addend_rowflag && nvr > 0)
+                     ? __ldg(reinterpret_cast<const unsigned *>(a.addend_rowflag + r0) + i) : 0xffffffffu;
+    unsigned rb = 0, re = 0;
+    if (sub < nvr) {
+        rb = __ldg(a.rowptr + r0 + sub);
+        re = __ldg(a.rowptr + r0 + sub + 1);
     }
-    int chunk_beg = 0, chunk_end = 0;
-    if (nvr > 0) {
-        chunk_beg = (int)(__ldg(a.rowptr + r0) & 0x7fffffffu);
-        chunk_end = (int)(__ldg(a.rowptr + r0 + nvr) & 0x7fffffffu);
-    }
+    const bool my_long = (rb >> 31) != 0;
+    const int my_beg = (int)(rb & 0x7fffffffu);
+    int my_end = (int)(re & 0x7fffffffu);
+    int chunk_beg = __shfl_sync(0xffffffffu, my_beg, 0, G::LANES);
+    int chunk_end = __shfl_sync(0xffffffffu, my_end, nvr > 0 ? nvr - 1 : 0, G::LANES);
+    if (nvr == 0) chunk_beg = chunk_end = 0;
+    if (sub >= nvr) my_end = INT_MAX;                    // sentinel: never passed
+    const unsigned long_bits = (__ballot_sync(0xffffffffu, my_long) >> gshift) & gbits;
 
     const int n_e = chunk_end - chunk_beg;
     int max_n = n_e;
@@ -273,28 +273,42 @@ __global__ void __launch_bounds__(kThreads, LGCN_SPMM_MINBLOCKS) spmm_chunk_kern
         const int cnt = min(n_e - t, G::LANES);           // entries of this tile (may be <= 0)
         const int maxcnt = min(G::LANES, max_n - t);      // warp-uniform
         for (int j = 0; j < maxcnt; j += U) {
+            // Unconditional loads: slots past the end carry col 0 (a valid, cache-resident row).  A
+            // predicated 128-bit load makes ptxas stage through 4 temporaries and serialises the
+            // batch (ncu: stalls on the predicated MOVs).
+            if (XF) {
+                // sparse-input hop (x = g' of the first backward hop): rows flagged all-zero are
+                // redirected to the cache-resident zero row; all flag loads of the batch first
+                int cjs[U];
+                unsigned xfl[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                // unconditional: slots past the end carry col 0 (a valid, cache-resident row).  A
-                // predicated 128-bit load makes ptxas stage through 4 temporaries and serialises
-                // the batch (ncu: stalls on the predicated MOVs).  Rows flagged all-zero (XF: the
-                // sparse g' of the first backward hop) are redirected to the zero row likewise.
-                const int cj = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
-                const float *src = a.x + (size_t)cj * D + sub * 4;
-                if (XF) src = __ldg(a.x_rowflag + cj) ? src : a.zero_row + sub * 4;
+                for (int u = 0; u < U; ++u) {
+                    cjs[u] = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
+                    xfl[u] = (unsigned)__ldg(a.x_rowflag + cjs[u]);
+                }
 #pragma unroll
-                for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
+                for (int u = 0; u < U; ++u) {
+                    const float *src = xfl[u] ? a.x + (size_t)cjs[u] * D + sub * 4 : a.zero_row + sub * 4;
+#pragma unroll
+                    for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int cj = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
+                    const float *src = a.x + (size_t)cj * D + sub * 4;
+#pragma unroll
+                    for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
+                }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const float wj = __int_as_float(__shfl_sync(0xffffffffu, cv.y, j + u, G::LANES));
                 const int e = chunk_beg + t + j + u;
                 // rows of this chunk that end at or before e (one ballot, no per-row pointer chase)
-                int row = 0;
-#pragma unroll
-                for (int i = 0; i < C::RPL; ++i)
-                    row += __popc((__ballot_sync(0xffffffffu, my_end[i] <= e) >> gshift) & gbits);
+                const unsigned passed = (__ballot_sync(0xffffffffu, my_end <= e) >> gshift) & gbits;
                 if (j + u < cnt) {
+                    const int row = __popc(passed);
                     if (row != cur) {                     // flush the finished row, zero the empty ones
 #pragma unroll
                         for (int v = 0; v < G::VEC; ++v) {
@@ -323,12 +337,12 @@ __global__ void __launch_bounds__(kThreads, LGCN_SPMM_MINBLOCKS) spmm_chunk_kern
             for (int v = 0; v < G::VEC; ++v) st_f4(stage + r * D + sub * 4 + v * G::LANES * 4, zero4);
     }
     __syncwarp();
-    chunk_epilogue<D, MODE, RSEL, HINT>(a, stage, r0, nvr, long_bits, pol);
+    chunk_epilogue<D, MODE, RSEL, HINT>(a, stage, r0, nvr, long_bits, pol, rfw);
 }
 
 // ---- long rows: one worker per segment, partial sums to seg_ws -----------------------------
 template <int D>
-__global__ void __launch_bounds__(kThreads) spmm_long_seg_kernel(const lgcn_spmm_args a) {
+__global__ void __launch_bounds__(kThreads) spmm_long_seg_kernel(const __grid_constant__ lgcn_spmm_args a) {
     using G = RowGeom<D>;
     const int lane = threadIdx.x & 31;
     const int grp = lane / G::LANES;
@@ -365,11 +379,16 @@ __global__ void __launch_bounds__(kThreads) spmm_long_seg_kernel(const lgcn_spmm
             for (int u = 0; u < kUnroll; ++u)
 #pragma unroll
                 for (int v = 0; v < G::VEC; ++v) x[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            int cjs[kUnroll];
+            unsigned xfl[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                const int cj = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
-                const float *src = a.x + (size_t)cj * D + sub * 4;
-                if (a.x_rowflag) src = __ldg(a.x_rowflag + cj) ? src : a.zero_row + sub * 4;
+                cjs[u] = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
+                xfl[u] = a.x_rowflag ? (unsigned)__ldg(a.x_rowflag + cjs[u]) : 1u;
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const float *src = xfl[u] ? a.x + (size_t)cjs[u] * D + sub * 4 : a.zero_row + sub * 4;
 #pragma unroll
                 for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
             }
@@ -392,7 +411,7 @@ __global__ void __launch_bounds__(kThreads) spmm_long_seg_kernel(const lgcn_spmm
 
 // ---- long rows: combine the segment partials in order, then the epilogue -------------------
 template <int D, int MODE>
-__global__ void __launch_bounds__(kThreads) spmm_long_combine_kernel(const lgcn_spmm_args a) {
+__global__ void __launch_bounds__(kThreads) spmm_long_combine_kernel(const __grid_constant__ lgcn_spmm_args a) {
     using G = RowGeom<D>;
     const int lane = threadIdx.x & 31;
     const int grp = lane / G::LANES;

@@ -89,7 +89,7 @@ class LightGCNEngine:
         self.G2 = torch.zeros_like(self.P)          # regulariser grad (+ g/(K+1) w/o fusion)
         # 1 = row received a gradient this step (G1/G2 are zero elsewhere): lets the backward
         # hops skip the gathers / addend reads of all-zero rows
-        self.rowflag = torch.zeros(self.N, dtype=torch.uint8, device=self.dev)
+        self.rowflag = torch.zeros(self.N + 32, dtype=torch.uint8, device=self.dev)   # padded
         self.zero_row = torch.zeros(256, dtype=torch.float32, device=self.dev)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.adam_scalars = torch.zeros(2, dtype=torch.float32, device=self.dev)
@@ -171,11 +171,13 @@ class LightGCNEngine:
         rf, zr = self.rowflag, self.zero_row
         for k in range(hops):
             # hop 0 gathers g' itself (<= 3*batch non-zero rows): flagged gathers
+            # (skipping the all-zero ADDEND rows the same way was measured neutral-to-slower:
+            # the addend is a perfectly coalesced stream, so it is read densely)
             acc = ops.spmm(g, acc, out=self.work[k % 2] if K > 1 else self.F, addend=self.G1,
-                           x_rowflag=rf if k == 0 else None, addend_rowflag=rf, zero_row=zr)
+                           x_rowflag=rf if k == 0 else None, zero_row=zr)
         if nofus:
             ops.spmm_adam(g, acc, self.P, self.m, self.v, self.adam_scalars, addend=self.G2,
-                          betas=self.betas, eps=self.eps, addend_rowflag=rf, zero_row=zr)
+                          betas=self.betas, eps=self.eps)
         else:
             f = self.fusion
             f["gW"].zero_()

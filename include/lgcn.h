@@ -115,7 +115,8 @@ typedef struct lgcn_spmm_args {
     /* Sparse-gradient shortcuts of the backward pass (all optional, NULL = dense):
      * x_rowflag[c] == 0 means row c of x is all zero, so its gather is skipped (mode ADD only;
      * the first Horner hop reads g', which has at most 3*batch non-zero rows);
-     * addend_rowflag[r] == 0 means row r of addend (and addend2) is all zero and is not read.
+     * addend_rowflag[r] == 0 means row r of addend (and addend2) is all zero and is not read;
+     * this array must be 4-byte aligned and padded to n_rows rounded up to a multiple of 16.
      * zero_row: a zero-filled device buffer of >= d floats the skipped loads are redirected to
      * (required when either flag array is given). */
     const uint8_t *x_rowflag;

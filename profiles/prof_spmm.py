@@ -27,6 +27,14 @@ N = U + I + B
 x = torch.randn((N, d), device=dev)
 y = torch.empty_like(x)
 add = torch.randn((N, d), device=dev) if mode != "plain" else None
+if mode == "hop1":        # the first Horner hop: x = g' has 3*2048 non-zero rows, flagged
+    rows = torch.randint(0, N, (6144,), device=dev)
+    x.zero_()
+    x[rows] = torch.randn((6144, d), device=dev)
+    flag = torch.zeros(N, dtype=torch.uint8, device=dev)
+    flag[rows] = 1
+    zero_row = torch.zeros(256, device=dev)
+    add = x
 torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
 ev[0].record()
@@ -35,6 +43,8 @@ for i in range(n):
         ops.spmm(g, x, out=y)
     elif mode == "add":
         ops.spmm(g, x, out=y, addend=add)
+    elif mode == "hop1":
+        ops.spmm(g, x, out=y, addend=add, x_rowflag=flag, addend_rowflag=flag, zero_row=zero_row)
     elif mode == "mean":
         ops.spmm(g, x, out=y, mean_layers=[add, x, add, x][:K])
     ev[i + 1].record()
