@@ -52,6 +52,7 @@ _SIGNATURES = {
     "lgcn_adam": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_f32, c_f32, c_f32,
                                  c_vp]),
     "lgcn_fusion_proj_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
+    "lgcn_fusion_force_simt": (None, [ctypes.c_int]),
     "lgcn_fusion_proj_bwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp,
                                             c_vp, c_vp, c_vp]),
     "lgcn_score_topk_workspace": (ctypes.c_size_t, [c_i64, c_i64, c_i32, c_i32]),

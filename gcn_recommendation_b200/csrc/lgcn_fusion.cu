@@ -263,6 +263,12 @@ static int fusion_bwd_launch(const float *Eid, const float *C, const float *W, c
 
 }  // namespace lgcn
 
+extern "C" int lgcn_fusion_fwd_tc_try(const float *Eid, const float *C, const float *W, const float *b,
+                                      int64_t n_items, int32_t d, int32_t c, float *H, cudaStream_t st);
+static int g_fusion_force_simt = 0;
+// test hook: 1 = always use the fp32 SIMT kernels (the tensor-core path is the default)
+extern "C" LGCN_API void lgcn_fusion_force_simt(int on) { g_fusion_force_simt = on; }
+
 extern "C" int lgcn_fusion_proj_fwd(const float *Eid, const float *C, const float *W,
                                     const float *b, int64_t n_items, int32_t d, int32_t c,
                                     float *H, lgcn_stream_t stream) {
@@ -273,6 +279,10 @@ extern "C" int lgcn_fusion_proj_fwd(const float *Eid, const float *C, const floa
     if (n_items == 0) return 0;
     if ((n_items + FM - 1) / FM > 0x7fffffffLL) return LGCN_E_TOO_LARGE;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (!(g_fusion_force_simt)) {           // tensor-core 3xTF32 path (lgcn_fusion_tc.cu)
+        const int rc = lgcn_fusion_fwd_tc_try(Eid, C, W, b, n_items, d, c, H, st);
+        if (rc != -100) return rc;
+    }
     switch (d) {
         case 16:  return fusion_fwd_launch<16>(Eid, C, W, b, n_items, c, H, st);
         case 32:  return fusion_fwd_launch<32>(Eid, C, W, b, n_items, c, H, st);

@@ -1,0 +1,318 @@
+// lgcn_fusion_tc.cu -- LightGCN_Fusion item block on the 5th-gen tensor cores (sm_100a).
+//
+// Replaces reference models/lightgcn_fusion.py:45-49 (forward):
+//     H = leaky_relu( cat([E_id, C], 1) @ W.T + b ),   W: [d, d+c],  c = 768
+// fp32-faithful (<= 1e-5) on tensor cores by the 3xTF32 split: x = hi + lo with hi = x truncated
+// to 10 mantissa bits (exact), lo = x - hi, and  x.w ~= hi.whi + lo.whi + hi.wlo  (the dropped
+// lo.wlo term and the truncation of lo are ~2^-21 relative).  The concatenation is never
+// materialised and the 13.5 GB content matrix is streamed exactly once.
+//
+// CTA (persistent over 128-item tiles): 8 loader warps read fp32 rows (E_id for k < d, content
+// for k >= d; W rows likewise), split them and write hi / lo straight into the UMMA canonical
+// K-major no-swizzle layout in shared memory (generic-proxy stores + fence.proxy.async); one
+// thread issues 12 tcgen05.mma.kind::tf32 (128 x d x 8) per 32-wide K chunk into one of two TMEM
+// accumulators; 4 epilogue warps (thread <-> item <-> TMEM lane) add the bias, apply the leaky
+// relu and store the row.  3-stage ring, mbarrier full/empty, tcgen05.commit.
+#include <float.h>
+
+#include "lgcn_common.cuh"
+
+namespace lgcn {
+namespace ftc {
+
+constexpr int MT = 128;            // items per tile (UMMA M)
+constexpr int KC = 32;             // K chunk (floats) = 8 core-matrix columns of 4 tf32
+constexpr int NSTAGE = 3;
+constexpr int LOADER_WARPS = 8;
+constexpr int kThreads = (LOADER_WARPS + 1 + 4) * 32;   // loaders, MMA issuer, epilogue
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// K-major, no swizzle: core matrix = 8 rows x 16 bytes (4 tf32) contiguous; SBO between 8-row
+// groups, LBO between the two 16-byte K columns of one K=8 instruction.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// D fp32 (bits 4-5 = 1), A/B tf32 (format 2 at bits 7-9 / 10-12), K-major, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
+}
+
+template <int D>
+struct Smem {
+    // per stage: [hi | lo] for A (128 x 32) and B (D x 32), canonical layout
+    float A[NSTAGE][2][MT * KC];
+    float B[NSTAGE][2][D * KC];
+    unsigned long long full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void split_store(float *hi_dst, float *lo_dst, const float4 &x) {
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
+    *reinterpret_cast<float4 *>(hi_dst) = h;
+    *reinterpret_cast<float4 *>(lo_dst) = l;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 1)
+fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm,
+                     const float *__restrict__ W, const float *__restrict__ bias, int64_t n_items,
+                     int c, float *__restrict__ H) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem<D> &sm = *reinterpret_cast<Smem<D> *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kin = D + c;
+    const int n_chunks = kin / KC;
+    const int64_t n_tiles = (n_items + MT - 1) / MT;
+    constexpr uint32_t SBO = 128;
+    constexpr uint32_t LBO_A = (MT / 8) * 128;      // bytes between K columns of A
+    constexpr uint32_t LBO_B = (D / 8) * 128;
+    constexpr uint32_t IDESC = make_idesc(D);
+    constexpr int TMEM_COLS = 2 * D < 32 ? 32 : 2 * D;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(smem_u32(&sm.full[s]), LOADER_WARPS);
+            mbar_init(smem_u32(&sm.empty[s]), 1);
+        }
+        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&sm.tfull[b]), 1); mbar_init(smem_u32(&sm.tempty[b]), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == LOADER_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&sm.tmem_base)), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+
+    if (warp < LOADER_WARPS) {
+        // ===== loaders: fp32 rows -> hi/lo tf32 in the canonical layout =====
+        // a warp task = 8 rows x 4 pieces (64 B per row): lanes 0-7 take rows, lane/8 the piece,
+        // so global reads are full sectors and the 16-byte smem stores are conflict free.
+        // The loads of chunk i+1 are issued before chunk i is split and stored (register
+        // prefetch): a loader warp would otherwise serialise on one HBM latency per chunk.
+        const int rl = lane & 7, pq = lane >> 3;
+        constexpr int NBT = (D / 8) * 2 / LOADER_WARPS;          // B tasks per warp
+        auto load_chunk = [&](int64_t tile, int ch, float4 (&xa)[4], float4 (&xb)[NBT]) {
+            const int64_t i0 = tile * MT;
+            const int k0 = ch * KC;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int task = warp * 4 + j;
+                const int r = (task >> 1) * 8 + rl;
+                const int k = k0 + ((task & 1) * 4 + pq) * 4;
+                const int64_t item = i0 + r;
+                xa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (item < n_items)
+                    xa[j] = (k < D) ? ld_nc_f4(Eid + (size_t)item * D + k)
+                                    : ld_stream_f4(Cm + (size_t)item * c + (k - D));
+            }
+#pragma unroll
+            for (int j = 0; j < NBT; ++j) {
+                const int task = warp * NBT + j;
+                const int r = (task >> 1) * 8 + rl;
+                xb[j] = ld_nc_f4(W + (size_t)r * kin + k0 + ((task & 1) * 4 + pq) * 4);
+            }
+        };
+        // three register buffers: chunks i (being stored), i+1 and i+2 (in flight)
+        float4 xa[4], xb[NBT], ya[4], yb[NBT], za[4], zb[NBT];
+        auto advance = [&](int64_t &t, int &c_) {
+            if (++c_ == n_chunks) { c_ = 0; t += gridDim.x; }
+        };
+        int64_t tile = blockIdx.x, t1 = tile, t2;
+        int ch = 0, c1 = 0, c2;
+        if (tile < n_tiles) load_chunk(tile, 0, xa, xb);
+        advance(t1, c1);
+        if (t1 < n_tiles) load_chunk(t1, c1, ya, yb);
+        t2 = t1; c2 = c1;
+        uint32_t it = 0;
+        while (tile < n_tiles) {
+            advance(t2, c2);
+            if (t2 < n_tiles) load_chunk(t2, c2, za, zb);
+            const int s = it % NSTAGE;
+            mbar_wait(smem_u32(&sm.empty[s]), ((it / NSTAGE) & 1) ^ 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int task = warp * 4 + j;
+                const int r = (task >> 1) * 8 + rl;
+                const int kq = (task & 1) * 4 + pq;
+                const int off = kq * (MT / 8) * 32 + (r >> 3) * 32 + (r & 7) * 4;   // floats
+                split_store(&sm.A[s][0][off], &sm.A[s][1][off], xa[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < NBT; ++j) {
+                const int task = warp * NBT + j;
+                const int r = (task >> 1) * 8 + rl;
+                const int kq = (task & 1) * 4 + pq;
+                const int off = kq * (D / 8) * 32 + (r >> 3) * 32 + (r & 7) * 4;
+                split_store(&sm.B[s][0][off], &sm.B[s][1][off], xb[j]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sm.full[s]));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { xa[j] = ya[j]; ya[j] = za[j]; }
+#pragma unroll
+            for (int j = 0; j < NBT; ++j) { xb[j] = yb[j]; yb[j] = zb[j]; }
+            tile = t1; ch = c1;
+            t1 = t2; c1 = c2;
+            ++it;
+        }
+        (void)ch;
+    } else if (warp == LOADER_WARPS) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t it = 0, tl = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+                const int acc = tl & 1;
+                mbar_wait(smem_u32(&sm.tempty[acc]), ((tl >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int ch = 0; ch < n_chunks; ++ch, ++it) {
+                    const int s = it % NSTAGE;
+                    mbar_wait(smem_u32(&sm.full[s]), (it / NSTAGE) & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(&sm.A[s][0][0]), a_lo = smem_u32(&sm.A[s][1][0]);
+                    const uint32_t b_hi = smem_u32(&sm.B[s][0][0]), b_lo = smem_u32(&sm.B[s][1][0]);
+#pragma unroll
+                    for (int kk = 0; kk < KC / 8; ++kk) {
+                        const uint64_t ah = make_smem_desc(a_hi + kk * 2 * LBO_A, LBO_A, SBO);
+                        const uint64_t al = make_smem_desc(a_lo + kk * 2 * LBO_A, LBO_A, SBO);
+                        const uint64_t bh = make_smem_desc(b_hi + kk * 2 * LBO_B, LBO_B, SBO);
+                        const uint64_t bl = make_smem_desc(b_lo + kk * 2 * LBO_B, LBO_B, SBO);
+                        const uint32_t d_addr = tmem_base + acc * D;
+                        tc_mma_tf32(d_addr, al, bh, IDESC, (ch > 0 || kk > 0) ? 1u : 0u);   // small terms first
+                        tc_mma_tf32(d_addr, ah, bl, IDESC, 1u);
+                        tc_mma_tf32(d_addr, ah, bh, IDESC, 1u);
+                    }
+                    tc_commit(smem_u32(&sm.empty[s]));
+                }
+                tc_commit(smem_u32(&sm.tfull[acc]));
+            }
+        }
+    } else {
+        // ===== epilogue: thread <-> item <-> TMEM lane =====
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;
+        uint32_t tl = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+            const int acc = tl & 1;
+            mbar_wait(smem_u32(&sm.tfull[acc]), (tl >> 1) & 1);
+            tc_fence_after();
+            const int64_t item = tile * MT + r;
+#pragma unroll 1
+            for (int cb = 0; cb < D / 32; ++cb) {
+                float v[32];
+                tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * D + cb * 32), v);
+                if (item < n_items) {
+                    float *dst = H + (size_t)item * D + cb * 32;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        float4 o;
+                        o.x = v[i] + __ldg(bias + cb * 32 + i);
+                        o.y = v[i + 1] + __ldg(bias + cb * 32 + i + 1);
+                        o.z = v[i + 2] + __ldg(bias + cb * 32 + i + 2);
+                        o.w = v[i + 3] + __ldg(bias + cb * 32 + i + 3);
+                        o.x = o.x > 0.f ? o.x : 0.01f * o.x;
+                        o.y = o.y > 0.f ? o.y : 0.01f * o.y;
+                        o.z = o.z > 0.f ? o.z : 0.01f * o.z;
+                        o.w = o.w > 0.f ? o.w : 0.01f * o.w;
+                        st_f4(dst + i, o);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sm.tempty[acc]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == LOADER_WARPS) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+template <int D>
+int launch_fwd(const float *Eid, const float *C, const float *W, const float *b, int64_t n_items, int c,
+               float *H, cudaStream_t st) {
+    static bool done = false;
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(fusion_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(Smem<D>));
+        if (e != cudaSuccess) return (int)e;
+        done = true;
+    }
+    const int64_t tiles = (n_items + MT - 1) / MT;
+    const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+    fusion_fwd_tc_kernel<D><<<grid, kThreads, sizeof(Smem<D>), st>>>(Eid, C, W, b, n_items, c, H);
+    LGCN_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace ftc
+}  // namespace lgcn
+
+// used by lgcn_fusion.cu: returns -100 when the shape is not handled by the tensor-core path
+extern "C" __attribute__((visibility("hidden"))) int lgcn_fusion_fwd_tc_try(
+    const float *Eid, const float *C, const float *W, const float *b, int64_t n_items, int32_t d,
+    int32_t c, float *H, cudaStream_t st) {
+    using namespace lgcn::ftc;
+    if ((d != 64 && d != 128) || c % KC != 0 || n_items < MT) return -100;
+    return d == 64 ? launch_fwd<64>(Eid, C, W, b, n_items, c, H, st)
+                   : launch_fwd<128>(Eid, C, W, b, n_items, c, H, st);
+}

@@ -198,6 +198,8 @@ LGCN_API int lgcn_adam(float *p, const float *g0, const float *g1, float *m, flo
 LGCN_API int lgcn_fusion_proj_fwd(const float *Eid, const float *C, const float *W, const float *b,
                          int64_t n_items, int32_t d, int32_t c, float *H,
                          lgcn_stream_t stream);
+/* test / debugging hook: 1 = force the fp32 SIMT kernels instead of the tcgen05 3xTF32 path */
+LGCN_API void lgcn_fusion_force_simt(int on);
 LGCN_API int lgcn_fusion_proj_bwd(const float *Eid, const float *C, const float *W, const float *H,
                          const float *gH, int64_t n_items, int32_t d, int32_t c, float *gEid,
                          float *gW, float *gb, lgcn_stream_t stream);
