@@ -48,6 +48,8 @@ _SIGNATURES = {
     "lgcn_bpr_apply": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_f32,
                                       c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "lgcn_zero_rows": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_vp]),
+    "lgcn_sample_bpr": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, ctypes.c_uint64, c_vp, c_i64, c_vp,
+                                       c_vp, c_vp, c_i64, c_vp]),
     "lgcn_adam_tick": (ctypes.c_int, [c_vp, c_vp, c_f32, c_f32, c_f32, c_vp]),
     "lgcn_adam": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_f32, c_f32, c_f32,
                                  c_vp]),

@@ -246,6 +246,24 @@ class LightGCNEngine:
             self._step_body()
         return self.loss
 
+    def train_steps(self, n_steps, seed=42, use_graph=False):
+        """``n_steps`` training steps on batches drawn by the device-side sampler (replaces the
+        reference's DataLoader, ``main.py:462-464,488``): nothing crosses the PCIe bus.  Returns
+        the device loss of the last step."""
+        if not hasattr(self, "sampler_state"):
+            self.sampler_state = torch.zeros(2, dtype=torch.int64, device=self.dev)
+            self.n_edges = int(self.g.rowptr[self.U].item())
+        for _ in range(n_steps):
+            ops.sample_bpr(self.g, self.U, self.I, self.n_edges, seed, self.sampler_state,
+                           self.b_users, self.b_pos, self.b_neg)
+            if use_graph:
+                if self._graph is None:
+                    self.capture()
+                self._graph.replay()
+            else:
+                self._step_body()
+        return self.loss
+
     def bpr_loss(self, users, pos, neg):
         """Loss only (no gradient, no update) on the current parameters."""
         F = self.propagate()

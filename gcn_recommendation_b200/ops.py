@@ -200,6 +200,17 @@ def zero_rows(t0, t1, users, pos, neg, num_users, rowflag=None):
                                      stream_ptr(t0.device)))
 
 
+def sample_bpr(g, num_users, num_items, n_edges, seed, state, users, pos, neg):
+    """Next batch of (user, pos, neg) triplets on the device (reference ``main.py:349-363``):
+    one epoch = a keyed random permutation of the training interactions, negatives uniform over
+    the user's non-interacted items.  ``state``: device int64[2] = {epoch, position}."""
+    COUNTERS["launches"] += 2
+    check(_lib.load().lgcn_sample_bpr(ptr(g.rowptr, "i32"), ptr(g.col, "i32"), num_users, num_items,
+                                      seed, ptr(state, "i64"), users.numel(), ptr(users, "i64"),
+                                      ptr(pos, "i64"), ptr(neg, "i64"), n_edges,
+                                      stream_ptr(users.device)))
+
+
 def adam_tick(step_dev, scalars, lr, betas=(0.9, 0.999)):
     COUNTERS["launches"] += 1
     check(_lib.load().lgcn_adam_tick(ptr(step_dev, "i64"), ptr(scalars), lr, betas[0], betas[1],

@@ -178,6 +178,19 @@ LGCN_API int lgcn_zero_rows(float *t0, float *t1, uint8_t *rowflag, const int64_
                    int64_t item_offset, lgcn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * f1  Device-side BPR batch sampler.
+ * Replaces: BPRDataset.__getitem__ + DataLoader(shuffle=True) (reference main.py:349-363,
+ * 462-464).  rowptr/col: the UNFLAGGED CSR of the graph (rows [0,num_users) hold the training
+ * interactions, columns = num_users + item, ascending); n_edges = rowptr[num_users].
+ * state (device int64[2]) = {epoch, position in epoch}; every call emits the next bs
+ * interactions of a keyed random permutation of the epoch (each interaction exactly once per
+ * epoch) with a uniform negative the user has not interacted with, then advances state.
+ * ------------------------------------------------------------------------------------- */
+LGCN_API int lgcn_sample_bpr(const int32_t *rowptr, const int32_t *col, int64_t num_users,
+                    int64_t num_items, uint64_t seed, int64_t *state, int64_t bs, int64_t *users,
+                    int64_t *pos, int64_t *neg, int64_t n_edges, lgcn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * a5  Dense Adam (torch.optim.Adam defaults, reference main.py:469,526).
  * lgcn_adam_tick: t += 1 on the device and refresh adam_scalars = {lr/(1-b1^t),
  * sqrt(1-b2^t)} (step counter and scalars stay on the device so a step is graph-capturable).

@@ -463,3 +463,48 @@ def test_feature_sharded_step_emulated_on_one_gpu(golden, dev):
                           g["final/brand_embedding.weight"]], 0)
     mx, fro = rel_err(P, ref)
     assert mx < 1e-3 and fro < 1e-5
+
+
+# ---------------------------------------------------------------------------- f1 sampler
+def test_device_sampler_epoch_is_a_permutation_with_valid_negatives(dev):
+    from gcn_recommendation_b200 import ops, synth
+    from gcn_recommendation_b200.graph import NormAdjCSR
+    inter = synth.generate("small", seed=4)
+    tu, ti, _, _ = inter.split_validation()
+    U, I, B = inter.num_users, inter.num_items, inter.num_brands
+    csr = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev)
+    E = len(tu)
+    assert int(csr.rowptr[U].item()) == E
+    bs = 1000
+    state = torch.zeros(2, dtype=torch.int64, device=dev)
+    u = torch.empty(bs, dtype=torch.int64, device=dev)
+    p = torch.empty_like(u)
+    n = torch.empty_like(u)
+    pairs, negs = [], []
+    steps = -(-E // bs)
+    for _ in range(steps):
+        ops.sample_bpr(csr, U, I, E, 7, state, u, p, n)
+        pairs.append((u * I + p).cpu().numpy())
+        negs.append((u.cpu().numpy(), n.cpu().numpy()))
+    keys = np.concatenate(pairs)
+    truth = np.sort(tu * I + ti)
+    # the first E samples are one epoch: every training interaction exactly once
+    assert np.array_equal(np.sort(keys[:E]), truth)
+    assert state.cpu().tolist() == [1, steps * bs - E]
+    posset = set(truth.tolist())
+    allu = np.concatenate([a for a, _ in negs])
+    alln = np.concatenate([b for _, b in negs])
+    assert alln.min() >= 0 and alln.max() < I
+    assert not any((int(a) * I + int(b)) in posset for a, b in zip(allu, alln))
+    # negatives are spread over the catalogue; the order inside an epoch is not the CSR order
+    assert len(np.unique(alln)) > 0.9 * I
+    assert not np.array_equal(keys[:E], truth)
+
+
+def test_engine_trains_from_device_sampler(golden, dev):
+    g = golden("tiny_lightgcn_d64_k3")
+    model = _model(g, "tiny_lightgcn_d64_k3", dev)
+    eng = model.engine(_graph(g, dev), batch_size=256)
+    first = eng.train_steps(1).item()
+    last = eng.train_steps(60).item()
+    assert abs(first - 0.6931) < 5e-3 and last < first - 1e-3       # ln 2 at init, then it learns
