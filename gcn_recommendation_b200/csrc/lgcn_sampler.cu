@@ -61,7 +61,7 @@ sample_bpr_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict_
     uint64_t ctr = mix64(seed ^ 0x5851f42d4c957f2dull) ^ ((uint64_t)epoch << 40) ^ (uint64_t)at;
     for (int attempt = 0; attempt < 64; ++attempt) {
         ctr = mix64(ctr + (uint64_t)attempt);
-        const int64_t cand = (int64_t)(((ctr >> 11) * (uint64_t)num_items) >> 53);   // uniform in [0, I)
+        const int64_t cand = (int64_t)__umul64hi(ctr, (uint64_t)num_items);          // uniform in [0, I)
         const int key = (int)(cand + num_users);
         int a = beg, b = end;                                   // binary search in the sorted row
         while (a < b) {
