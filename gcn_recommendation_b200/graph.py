@@ -10,6 +10,8 @@ Layout in HBM (one graph): ``rowptr`` int32[N+1], ``col`` int32[nnz] (ascending 
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -33,6 +35,9 @@ class NormAdjCSR:
         self.nnz = int(col.numel())
         self.device = rowptr.device
         self._seg_ws = {}
+        if long_row_threshold is None and os.environ.get("LGCN_LONG_ROW_THRESHOLD"):
+            long_row_threshold = int(os.environ["LGCN_LONG_ROW_THRESHOLD"])      # tuning hook
+            seg_len = int(os.environ.get("LGCN_SEG_LEN", max(long_row_threshold // 2, 8)))
         if long_row_threshold is None:
             # small graphs are latency bound: shorter sequential chains, more workers
             small = self.n_rows < SMALL_GRAPH_ROWS
