@@ -30,8 +30,8 @@ namespace tc {
 
 constexpr int MT = 128;        // users per CTA (UMMA M)
 constexpr int NT = 128;        // items per tile (UMMA N)
-constexpr int NSTAGE = 2;      // item-tile ring
-constexpr int CAND = 128;      // candidates kept per user (all epilogue groups together)
+constexpr int NSTAGE = 3;      // item-tile ring
+constexpr int CAND = 96;       // candidates kept per user (all epilogue groups together)
 constexpr int NB = 4;          // TMEM accumulator buffers == epilogue groups (tile t -> group t % NB)
 constexpr int GCAND = CAND / NB;             // heap entries per (user, group)
 constexpr int kThreads = 64 + NB * 128;      // warp 0: copy producer, warp 1: MMA issuer, then NB

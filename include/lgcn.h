@@ -233,7 +233,7 @@ LGCN_API int lgcn_score_topk(const float *Fu, const float *Fi, const int64_t *us
                     const int32_t *mask_col, int32_t k, int32_t *out_ids, float *out_scores,
                     void *workspace, size_t workspace_bytes, lgcn_stream_t stream);
 /* Tensor-core path of the same operation for large catalogues (d = 64 or 128): a bf16
- * tcgen05.mma filter keeps 64 candidates per user (train items skipped in the epilogue), an
+ * tcgen05.mma filter keeps 96 candidates per user (train items skipped in the epilogue), an
  * exact fp32 re-score orders the top k, and fail[q] = 1 marks users whose result is not
  * CERTIFIED exact (k-th exact score within the bf16 error bound of the filter threshold);
  * the caller re-runs those through lgcn_score_topk.  lgcn_score_tc_prepare converts the item

@@ -69,3 +69,58 @@ def test_tc_near_tie_scores_fall_back_to_exact(dev):
     ids, sc = ops.score_topk(Fu, Fi, users, mr, mc, 20, tensor_cores=True)
     eids, esc = ops.score_topk_exact(Fu, Fi, users, mr, mc, 20)
     assert torch.equal(ids, eids)
+
+
+def test_amazon_shape_properties(dev):
+    """Size-independent checks at the FULL Amazon-Books-2023 shape (BASELINE.json configs[2]:
+    14.7 M nodes, 59 M entries, d=128): the normalised adjacency is symmetric, the SpMM is
+    deterministic and linear, the sparse-input hop with row flags equals the dense hop, and the
+    tensor-core rating returns descending scores, no masked item and the exact kernel's ids."""
+    from gcn_recommendation_b200 import ops, synth
+    from gcn_recommendation_b200.engine import build_mask_csr
+    from gcn_recommendation_b200.graph import NormAdjCSR
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~60 GB of free HBM")
+    U, I, B, total, d, K = synth.SHAPES["amazon"]
+    inter = synth.generate_device("amazon", dev, seed=0)
+    tu, ti, vu, vi = synth.split_validation_device(inter)
+    del inter
+    csr = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev)
+    N = U + I + B
+    assert csr.nnz == 2 * tu.numel() and csr.n_long > 0
+    gen = torch.Generator(device=dev).manual_seed(1)
+    x = torch.randn((N, d), device=dev, generator=gen)
+    y = torch.randn((N, d), device=dev, generator=gen)
+    ax = ops.spmm(csr, x)
+    ay = ops.spmm(csr, y)
+    lhs = (x.double() * ay.double()).sum().item()
+    rhs = (ax.double() * y.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), abs(rhs), 1.0)              # <x, A y> == <A x, y>
+    assert torch.equal(ax, ops.spmm(csr, x))                                     # deterministic
+    axy = ops.spmm(csr, (x + y).contiguous())
+    err = (axy - (ax + ay)).norm().item() / axy.norm().item()
+    assert err < 1e-5                                                            # linear
+    del ay, axy
+    # sparse-input hop: flagged gathers == dense gathers
+    rows = torch.randint(0, N, (6144,), device=dev, generator=gen)
+    xs = torch.zeros_like(x)
+    xs[rows] = x[rows]
+    flag = torch.zeros(N + 32, dtype=torch.uint8, device=dev)
+    flag[rows] = 1
+    zero_row = torch.zeros(256, device=dev)
+    dense = ops.spmm(csr, xs, addend=xs)
+    sparse = ops.spmm(csr, xs, addend=xs, x_rowflag=flag, zero_row=zero_row)
+    assert torch.equal(dense, sparse)
+    del dense, sparse, xs, y
+    # rating over the full 4.4 M-item catalogue
+    Fu, Fi = ax[:U], ax[U:U + I]
+    eu = vu[:256].contiguous()
+    mr, mc = build_mask_csr(eu.cpu().numpy(), tu.cpu().numpy(), ti.cpu().numpy(), U, dev)
+    ids, sc = ops.score_topk(Fu, Fi, eu, mr, mc, 20, tensor_cores=True)
+    eids, esc = ops.score_topk_exact(Fu, Fi, eu, mr, mc, 20)
+    assert torch.equal(ids, eids) and torch.equal(sc.view(torch.int32), esc.view(torch.int32))
+    assert bool((sc[:, :-1] >= sc[:, 1:]).all())
+    rp, cols, got = mr.cpu().numpy(), mc.cpu().numpy(), ids.cpu().numpy()
+    for q in range(256):
+        assert not set(got[q].tolist()) & set(cols[rp[q]:rp[q + 1]].tolist())
