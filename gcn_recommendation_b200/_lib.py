@@ -17,6 +17,9 @@ c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctyp
 
 SPMM_PLAIN, SPMM_ADD, SPMM_MEAN, SPMM_ADAM = 0, 1, 2, 3
 SPMM_F_STREAM_HINTS = 1
+SPMM_F_NO_RING = 2
+SPMM_F_BIG_PATH = 4
+SPMM_F_FORCE_RING = 16
 BPR_GP_INCLUDES_GF, BPR_NO_GRAD = 1, 2
 ABI_VERSION = 3
 

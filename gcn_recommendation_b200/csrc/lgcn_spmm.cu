@@ -19,6 +19,8 @@
 // all of its operand loads independent (mean of the earlier layers / Horner addend / Adam).
 #include <limits.h>
 
+#include <type_traits>
+
 #include "lgcn_common.cuh"
 
 namespace lgcn {
@@ -109,22 +111,21 @@ __device__ __forceinline__ void epilogue_row(const lgcn_spmm_args &a, int64_t ro
 }
 
 // ---- chunk epilogue: stream the staged rows, operand loads batched ahead of the math ------
-template <int D, int MODE, int RSEL, bool HINT>
+template <int D, int MODE, int R, bool HINT>
 __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const float *stage,
                                                int64_t r0, int nvr, unsigned long_bits, uint64_t pol,
-                                               const unsigned (&rfw)[ChunkCfg<D, RSEL>::R / 4]) {
+                                               const unsigned (&rfw)[R / 4]) {
     using G = RowGeom<D>;
-    using C = ChunkCfg<D, RSEL>;
     const int sub = (threadIdx.x & 31) % G::LANES;
     constexpr int B = (MODE == LGCN_SPMM_ADAM || MODE == LGCN_SPMM_MEAN) ? 2 : 4;  // rows per batch
-    static_assert(C::R % B == 0, "chunk rows must be a multiple of the epilogue batch");
+    static_assert(R % B == 0, "chunk rows must be a multiple of the epilogue batch");
     const float div = (float)(a.n_layers + 1);
     float ss = 0.f, bs = 1.f;
     if (MODE == LGCN_SPMM_ADAM) { ss = __ldg(a.adam_scalars); bs = __ldg(a.adam_scalars + 1); }
 #pragma unroll
     for (int v = 0; v < G::VEC; ++v) {
         const int coff = sub * 4 + v * G::LANES * 4;
-        for (int rb = 0; rb < C::R; rb += B) {
+        for (int rb = 0; rb < R; rb += B) {
             bool on[B];
             size_t off[B];
 #pragma unroll
@@ -341,7 +342,179 @@ spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
             for (int v = 0; v < G::VEC; ++v) st_f4(stage + r * D + sub * 4 + v * G::LANES * 4, zero4);
     }
     __syncwarp();
-    chunk_epilogue<D, MODE, RSEL, HINT>(a, stage, r0, nvr, long_bits, pol, rfw);
+    chunk_epilogue<D, MODE, C::R, HINT>(a, stage, r0, nvr, long_bits, pol, rfw);
+}
+
+// compile-time unrolled loop: f(std::integral_constant<int, I>) for I in [0, N)
+template <int N, int I = 0, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<N, I + 1>(f);
+    }
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// ---- ring kernel: the chunk walk of spmm_chunk_kernel with the gathers in a cp.async ring -------
+// One worker per chunk of R rows (R = 8: many small chunks, so that the rowptr -> {col,val} ->
+// gather start-up chain of one warp overlaps the streaming of the 20+ others on the SM), rows
+// staged in shared memory for the batched epilogue.  Measured at the Amazon shape (d = 128):
+// 4.36 ms at 83 % of the DRAM peak (ncu) against 6.0 ms / 60 % for the register-batch kernel.
+#ifndef LGCN_RING_WARPS
+#define LGCN_RING_WARPS 1
+#endif
+#ifndef LGCN_RING_S
+#define LGCN_RING_S 8
+#endif
+#ifndef LGCN_RING_R
+#define LGCN_RING_R 8
+#endif
+constexpr int kRingWarps = LGCN_RING_WARPS;
+
+template <int D>
+struct RingCfg {
+    using G = RowGeom<D>;
+    static constexpr int R = G::LANES < LGCN_RING_R ? G::LANES : LGCN_RING_R;   // one row end per lane
+    static constexpr int S = G::LANES < LGCN_RING_S ? G::LANES : LGCN_RING_S;   // ring slots (power of 2)
+    static constexpr int WORKERS = kRingWarps * G::GROUPS;
+    static constexpr int ROWS_PER_CTA = WORKERS * R;
+    static constexpr size_t SMEM = (size_t)WORKERS * (R + S) * D * sizeof(float);
+    static_assert((S & (S - 1)) == 0 && S >= 2 && S <= G::LANES, "ring depth");
+    static_assert(R % 4 == 0, "chunk rows");
+};
+
+template <int D, int MODE, bool HINT>
+__global__ void __launch_bounds__(kRingWarps * 32)
+spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
+    using G = RowGeom<D>;
+    using C = RingCfg<D>;
+    constexpr int L = G::LANES, S = C::S;
+    const uint64_t pol = HINT ? policy_evict_first() : 0ull;
+    extern __shared__ __align__(16) float ring_smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int grp = lane / L;
+    const int sub = lane % L;
+    const int gshift = grp * L;
+    const unsigned gbits = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
+    float *stage = ring_smem + (size_t)((warp * G::GROUPS + grp) * (C::R + S)) * D;
+    const float *ring = stage + C::R * D + sub * 4;                   // this lane's 16 bytes of slot 0
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+
+    const int64_t worker = ((int64_t)blockIdx.x * kRingWarps + warp) * G::GROUPS + grp;
+    const int64_t r0 = worker * C::R;
+    const int64_t left = a.n_rows - r0;
+    const int nvr = left <= 0 ? 0 : (left < C::R ? (int)left : C::R);
+
+    unsigned rfw[C::R / 4];
+#pragma unroll
+    for (int i = 0; i < C::R / 4; ++i)
+        rfw[i] = ((MODE == LGCN_SPMM_ADD || MODE == LGCN_SPMM_ADAM) && a.addend_rowflag && nvr > 0)
+                     ? __ldg(reinterpret_cast<const unsigned *>(a.addend_rowflag + r0) + i) : 0xffffffffu;
+    unsigned rb = 0, re = 0;
+    if (sub < nvr) {
+        rb = __ldg(a.rowptr + r0 + sub);
+        re = __ldg(a.rowptr + r0 + sub + 1);
+    }
+    const bool my_long = (rb >> 31) != 0;
+    const int my_beg = (int)(rb & 0x7fffffffu);
+    int my_end = (int)(re & 0x7fffffffu);
+    int chunk_beg = __shfl_sync(0xffffffffu, my_beg, 0, L);
+    int chunk_end = __shfl_sync(0xffffffffu, my_end, nvr > 0 ? nvr - 1 : 0, L);
+    if (nvr == 0) chunk_beg = chunk_end = 0;
+    const unsigned long_bits = (__ballot_sync(0xffffffffu, my_long) >> gshift) & gbits;
+    my_end = sub < nvr ? my_end - chunk_beg : INT_MAX;   // relative to the chunk stream; sentinel
+
+    const int n_e = chunk_end - chunk_beg;
+    int max_n = n_e;
+#pragma unroll
+    for (int off = L; off < 32; off <<= 1)
+        max_n = max(max_n, __shfl_xor_sync(0xffffffffu, max_n, off));
+
+    const char *xb = reinterpret_cast<const char *>(a.x + sub * 4);
+    const int2 *cvp = reinterpret_cast<const int2 *>(a.colval) + chunk_beg;
+    const int2 z2 = make_int2(0, 0);
+    int2 cvA = sub < n_e ? ld_cv<HINT>(cvp + sub, pol) : z2;                 // entries [t, t+L)
+    int2 cvB = L + sub < n_e ? ld_cv<HINT>(cvp + L + sub, pol) : z2;         // [t+L, t+2L)
+    int2 cvC = 2 * L + sub < n_e ? ld_cv<HINT>(cvp + 2 * L + sub, pol) : z2; // [t+2L, t+3L)
+    // Gather of stream entry t+JJ (tile-relative index JJ is a compile-time constant, so the source
+    // lane of the shuffle, the tile register and the ring slot are all immediates).
+    auto issue = [&](int t, auto jj_c) {
+        constexpr int JJ = decltype(jj_c)::value;
+        const int cj = __shfl_sync(0xffffffffu, JJ < L ? cvA.x : cvB.x, JJ % L, L);
+        if (t + JJ < n_e) {
+            const char *src = xb + (uint64_t)(uint32_t)cj * (D * 4);
+            const uint32_t dst = ring_s + (uint32_t)(JJ % S) * (D * 4);
+#pragma unroll
+            for (int v = 0; v < G::VEC; ++v) cp_async16(dst + v * L * 16, src + v * L * 16);
+        }
+        cp_async_commit();
+    };
+    static_for<S - 1>([&](auto i) { issue(0, i); });
+
+    float4 acc[G::VEC];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int v = 0; v < G::VEC; ++v) acc[v] = zero4;
+    int cur = 0;                                          // row (within the chunk) being summed
+    int cur_end = __shfl_sync(0xffffffffu, my_end, 0, L); // first stream entry past that row
+
+    for (int t = 0; t < max_n; t += L) {                  // cvA = entries [t,t+L), cvB = [t+L,t+2L)
+        bool done = false;
+        static_for<L>([&](auto j_c) {
+            constexpr int J = decltype(j_c)::value;
+            if (done) return;
+            const int e = t + J;
+            if (e >= max_n) { done = true; return; }      // warp-uniform
+            issue(t, std::integral_constant<int, J + S - 1>{});
+            cp_async_wait<S - 1>();                       // this lane's bytes of entry e have landed
+            const float wj = __int_as_float(__shfl_sync(0xffffffffu, cvA.y, J, L));
+            const bool live = e < n_e;
+            // leave every row that ends at or before e: the finished sum (zeros for the empty rows
+            // that follow it) goes to the staging buffer, one row per trip
+            while (G::GROUPS == 1 ? (e >= cur_end) : __any_sync(0xffffffffu, live && e >= cur_end)) {
+                const bool cross = G::GROUPS == 1 || (live && e >= cur_end);
+                if (cross) {
+#pragma unroll
+                    for (int v = 0; v < G::VEC; ++v) {
+                        st_f4(stage + cur * D + sub * 4 + v * L * 4, acc[v]);
+                        acc[v] = zero4;
+                    }
+                    ++cur;
+                }
+                cur_end = __shfl_sync(0xffffffffu, my_end, cur, L);
+            }
+            if (live) {
+                const float *slot = ring + (J % S) * D;
+#pragma unroll
+                for (int v = 0; v < G::VEC; ++v) {
+                    const float4 xv = *reinterpret_cast<const float4 *>(slot + v * L * 4);
+                    fma4(acc[v], wj, xv);
+                }
+            }
+        });
+        cvA = cvB;                                        // consume pointer leaves its tile
+        cvB = cvC;
+        cvC = t + 3 * L + sub < n_e ? ld_cv<HINT>(cvp + t + 3 * L + sub, pol) : z2;
+    }
+    cp_async_wait<0>();
+    // rows cur .. nvr-1: the last summed row, then trailing empty rows
+#pragma unroll 1
+    for (; cur < nvr; ++cur) {
+#pragma unroll
+        for (int v = 0; v < G::VEC; ++v) {
+            st_f4(stage + cur * D + sub * 4 + v * L * 4, acc[v]);
+            acc[v] = zero4;
+        }
+    }
+    __syncwarp();
+    chunk_epilogue<D, MODE, C::R, HINT>(a, stage, r0, nvr, long_bits, pol, rfw);
 }
 
 // ---- long rows: one worker per segment, partial sums to seg_ws -----------------------------
@@ -467,6 +640,23 @@ static int launch_chunks(const lgcn_spmm_args &a, cudaStream_t st) {
     return 0;
 }
 
+template <int D, int MODE, bool HINT>
+static int launch_ring(const lgcn_spmm_args &a, cudaStream_t st) {
+    using C = RingCfg<D>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(spmm_ring_kernel<D, MODE, HINT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    const int64_t gb = (a.n_rows + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
+    if (gb > 0x7fffffffLL) return LGCN_E_TOO_LARGE;
+    spmm_ring_kernel<D, MODE, HINT><<<(unsigned)gb, kRingWarps * 32, C::SMEM, st>>>(a);
+    LGCN_LAUNCH_CHECK();
+    return 0;
+}
+
 template <int D, int MODE>
 static int launch_mode(const lgcn_spmm_args &a, cudaStream_t st) {
     using G = RowGeom<D>;
@@ -479,11 +669,18 @@ static int launch_mode(const lgcn_spmm_args &a, cudaStream_t st) {
     if (a.n_rows > 0) {
         // small graphs: 4-row chunks so that the chip is filled (>= ~2 waves of workers)
         const int64_t big_workers = a.n_rows / ChunkCfg<D, 0>::R;
-        const bool small = big_workers < (int64_t)kNumSMs * 32 * G::GROUPS;
+        const bool small = big_workers < (int64_t)kNumSMs * 32 * G::GROUPS && !(a.flags & LGCN_SPMM_F_BIG_PATH);
         const bool hint = (a.flags & LGCN_SPMM_F_STREAM_HINTS) != 0;
         int rc;
         const bool xf = MODE == LGCN_SPMM_ADD && a.x_rowflag != nullptr;
-        if (xf) {               // sparse-input hop (first Horner hop): flagged gathers
+        // Large graphs: the cp.async ring kernel.  ADAM (its epilogue wants the registers) and the
+        // flagged first hop (zero-filling ring slots was measured slower: 6.4 vs 5.0 ms) keep the
+        // register-batch chunk kernel.
+        const bool ring = !small && !xf && !(a.flags & LGCN_SPMM_F_NO_RING) &&
+                          (MODE != LGCN_SPMM_ADAM || (a.flags & LGCN_SPMM_F_FORCE_RING));
+        if (ring) {
+            rc = hint ? launch_ring<D, MODE, true>(a, st) : launch_ring<D, MODE, false>(a, st);
+        } else if (xf) {        // sparse-input hop (first Horner hop): flagged gathers
             if (small) rc = launch_chunks<D, LGCN_SPMM_ADD, 1, false, true>(a, st);
             else if (hint) rc = launch_chunks<D, LGCN_SPMM_ADD, 0, true, true>(a, st);
             else rc = launch_chunks<D, LGCN_SPMM_ADD, 0, false, true>(a, st);

@@ -19,6 +19,7 @@ from ._lib import SPMM_ADAM, SPMM_ADD, SPMM_MEAN, SPMM_PLAIN, SpmmArgs, check, p
 COUNTERS = {"launches": 0}
 L2_STREAM_BYTES = 96 << 20      # tables larger than this are streamed with L2 evict_first hints
 PROFILE = None
+SPMM_FLAGS_EXTRA = 0           # OR-ed into lgcn_spmm_args.flags (tests / A-B measurements force a kernel)
 
 
 def _launch_spmm(a, g, dev, tag):
@@ -39,8 +40,9 @@ def _spmm_args(g, x, mode, d):
     a.rowptr, a.colval = ptr(g.rowptr_flagged, "i32"), g.colval.data_ptr()
     a.x = ptr(x)
     a.n_rows, a.d, a.mode = g.n_rows, d, mode
+    a.flags = SPMM_FLAGS_EXTRA
     if g.n_cols * d * 4 > L2_STREAM_BYTES:
-        a.flags = _lib.SPMM_F_STREAM_HINTS
+        a.flags |= _lib.SPMM_F_STREAM_HINTS
     if g.n_long > 0:
         a.n_long = g.n_long
         a.long_row_ids = ptr(g.long_row_ids, "i32")

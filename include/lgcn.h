@@ -127,6 +127,10 @@ typedef struct lgcn_spmm_args {
 /* tables do not fit L2: stream entries / outputs / epilogue operands with L2 evict_first so
  * that they do not displace the gathered rows (set by the host when n_cols*d*4 >> L2) */
 #define LGCN_SPMM_F_STREAM_HINTS 1
+/* kernel selection overrides for tests and A/B measurements (default: chosen by d and mode) */
+#define LGCN_SPMM_F_NO_RING 2       /* register-batch chunk kernel only                      */
+#define LGCN_SPMM_F_BIG_PATH 4      /* large-graph kernels even when the graph is small      */
+#define LGCN_SPMM_F_FORCE_RING 16   /* cp.async ring kernel for the ADAM epilogue too        */
 
 #define LGCN_SPMM_PLAIN 0 /* y = A x                                                    */
 #define LGCN_SPMM_ADD   1 /* y = addend + A x              (Horner backward hop)        */

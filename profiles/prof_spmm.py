@@ -16,6 +16,7 @@ workload = sys.argv[1] if len(sys.argv) > 1 else "amazon"
 mode = sys.argv[2] if len(sys.argv) > 2 else "plain"
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 dev = torch.device("cuda:0")
+ops.SPMM_FLAGS_EXTRA = int(os.environ.get("LGCN_SPMM_FLAGS", "0"))   # 2 = chunk kernel instead of ring
 U, I, B, total, d, K = synth.SHAPES[workload]
 if len(sys.argv) > 4:
     d = int(sys.argv[4])

@@ -99,6 +99,79 @@ def test_spmm_bit_exact_all_dims(dev, d):
     assert (deg == 0).any() and not Y[deg == 0].any()
 
 
+@pytest.mark.parametrize("d", [16, 32, 64, 128, 256])
+@pytest.mark.parametrize("kernel", ["ring", "chunk"])
+def test_spmm_large_graph_kernels_bit_exact(dev, d, kernel):
+    """The large-graph kernels (cp.async ring kernel / 16-row register-batch chunks) forced onto
+    a small graph: every epilogue bit-exact against the oracle, with short-row/long-row mixes,
+    empty rows and a ragged last worker."""
+    from gcn_recommendation_b200 import _lib, ops, synth
+    from gcn_recommendation_b200.graph import NormAdjCSR
+    orc = _orc()
+    U, I, B = 3001, 4003, 2
+    inter = synth.generate((U, I, B, 70_000), seed=100 + d)
+    tu, ti, _, _ = inter.split_validation()
+    a = orc.build_norm_adj(tu, ti, U, I, B)
+    N = U + I + B
+    rng = np.random.default_rng(d)
+    X = rng.standard_normal((N, d), dtype=np.float32)
+    A1 = rng.standard_normal((N, d), dtype=np.float32)
+    A2 = rng.standard_normal((N, d), dtype=np.float32)
+    ref = orc.spmm(a["rowptr"], a["col"], a["val"], X)
+    old = ops.SPMM_FLAGS_EXTRA
+    ops.SPMM_FLAGS_EXTRA = _lib.SPMM_F_BIG_PATH | (_lib.SPMM_F_NO_RING if kernel == "chunk"
+                                                      else _lib.SPMM_F_FORCE_RING)
+    try:
+        for thr in (0, 64):          # 0: every row on the sequential path; 64: hot items segmented
+            csr = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev, long_row_threshold=thr, seg_len=32)
+            short = np.diff(a["rowptr"]) <= (thr if thr else 1 << 30)
+            xt = _t(X, dev)
+            Y = ops.spmm(csr, xt).cpu().numpy()
+            assert np.array_equal(_bits(Y[short]), _bits(ref[short]))
+            assert rel_err(Y, ref)[0] < TOL
+            Ya = ops.spmm(csr, xt, addend=_t(A1, dev)).cpu().numpy()
+            assert np.array_equal(_bits(Ya[short]), _bits((A1 + ref)[short]))
+            Ym = ops.spmm(csr, xt, mean_layers=[_t(A1, dev), _t(A2, dev), xt]).cpu().numpy()
+            want = (((A1 + A2) + X) + ref) / np.float32(4)
+            assert np.array_equal(_bits(Ym[short]), _bits(want[short]))
+            assert rel_err(Ym, want)[0] < TOL
+        # sparse-input hop (first Horner hop): x has few non-zero rows, flagged; zero rows are
+        # never read (poisoned with NaN here to prove it)
+        for thr in (0, 64):
+            csr = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev, long_row_threshold=thr, seg_len=32)
+            short = np.diff(a["rowptr"]) <= (thr if thr else 1 << 30)
+            nzr = rng.choice(N, 600, replace=False)
+            Xs = np.zeros((N, d), np.float32)
+            Xs[nzr] = rng.standard_normal((600, d), dtype=np.float32)
+            flag = np.zeros(N + 32, np.uint8)
+            flag[nzr] = 1
+            Xp = Xs.copy()
+            Xp[flag[:N] == 0] = np.nan
+            zr = torch.zeros(256, device=dev)
+            Yx = ops.spmm(csr, _t(Xp, dev), addend=_t(A1, dev), x_rowflag=_t(flag, dev, torch.uint8),
+                          zero_row=zr).cpu().numpy()
+            want = A1 + orc.spmm(a["rowptr"], a["col"], a["val"], Xs)
+            assert np.array_equal(_bits(Yx[short]), _bits(want[short]))
+            assert rel_err(Yx, want)[0] < TOL
+        # Adam epilogue against the standalone Adam kernel fed with the same gradient
+        csr = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev, long_row_threshold=0)
+        xt = _t(X, dev)
+        p1, m1, v1 = (_t(rng.standard_normal((N, d), dtype=np.float32) * s, dev) for s in (1.0, 0.01, 0.0))
+        v1 = v1.abs() + 1e-4
+        p2, m2, v2 = p1.clone(), m1.clone(), v1.clone()
+        sc = torch.tensor([1e-3 / (1 - 0.9 ** 3), (1 - 0.999 ** 3) ** 0.5], device=dev)
+        gout = torch.empty((N, d), device=dev)
+        ops.spmm_adam(csr, xt, p1, m1, v1, sc, addend=_t(A1, dev), addend2=_t(A2, dev), g_out=gout)
+        gwant = (ref + A1) + A2
+        assert np.array_equal(_bits(gout.cpu().numpy()), _bits(gwant))
+        ops.SPMM_FLAGS_EXTRA = 0
+        ops.spmm_adam(csr, xt, p2, m2, v2, sc, addend=_t(A1, dev), addend2=_t(A2, dev))
+        for x1, x2 in ((p1, p2), (m1, m2), (v1, v2)):
+            assert torch.equal(x1, x2)
+    finally:
+        ops.SPMM_FLAGS_EXTRA = old
+
+
 @pytest.mark.parametrize("d", [64, 128])
 def test_spmm_long_row_plan_within_tolerance(dev, d):
     """Rows longer than the threshold are summed segment-wise: deterministic, <= 1e-5."""
