@@ -15,11 +15,17 @@
 //                             items with a cursor into the sorted mask list, and push scores
 //                             above the user's running threshold into a C-entry min-heap in
 //                             shared memory.  The [users x items] scores never leave the SM.
+//                             The heap key is not the bf16 score s but an UPPER BOUND of the exact
+//                             score: key = s + c_u * |v|, c_u = 1.05 * 2^-8 * |u| (bf16 rounding
+//                             of both operands: |s - u.v| <= (2^-8 + 2^-16) |u||v|), with the
+//                             item's own norm -- a window of 32 items is first tested against
+//                             its largest norm (one FMA per window), so the bound costs nothing
+//                             in the common case and is not inflated by the few high-norm items.
 //  3. score_refine_kernel   : exact fp32 score (sequential FMA over the features, the order of
 //                             the CPU oracle) of the C candidates, ordered top-k, and a per-user
-//                             certificate: exact_kth > threshold + eps_u with eps_u an upper
-//                             bound of the bf16 rounding error; users that fail are flagged and
-//                             re-run by the exact SIMT kernel (lgcn_score.cu).
+//                             certificate: every dropped item has exact <= key <= threshold, so
+//                             exact_kth > threshold proves the ids; users that fail are flagged
+//                             and re-run by the exact SIMT kernel (lgcn_score.cu).
 #include <cuda_bf16.h>
 #include <float.h>
 
@@ -123,11 +129,11 @@ struct FilterSmem {
     uint32_t tmem_base;
 };
 
-// ---- item table -> bf16 canonical tiles, max item norm -----------------------------------------
+// ---- item table -> bf16 canonical tiles, item norms -----------------------------------------
 template <int D>
 __global__ void __launch_bounds__(256)
 prepare_items_kernel(const float *__restrict__ Fi, int64_t n_items, int64_t n_pad,
-                     __nv_bfloat16 *__restrict__ Bt, unsigned int *__restrict__ vmax_bits) {
+                     __nv_bfloat16 *__restrict__ Bt, float *__restrict__ vnorm) {
     // one thread per (item, 8-feature chunk)
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     constexpr int KCH = D / 8;
@@ -152,7 +158,23 @@ prepare_items_kernel(const float *__restrict__ Fi, int64_t n_items, int64_t n_pa
     float s = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
 #pragma unroll
     for (int off = KCH / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (kc == 0) atomicMax(vmax_bits, __float_as_uint(sqrtf(s)));   // positive floats order as uints
+    // rounded up by one ulp-ish factor so that it is an upper bound of the true norm
+    if (kc == 0) vnorm[item] = sqrtf(s) * 1.000001f;
+}
+
+// largest item norm of every 32-item window (the granularity of the epilogue's tcgen05.ld)
+__global__ void __launch_bounds__(256)
+window_norm_kernel(const float *__restrict__ vnorm, int64_t n_windows, float *__restrict__ wnorm) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_windows) return;
+    const float4 *p = reinterpret_cast<const float4 *>(vnorm + w * 32);
+    float m = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 v = __ldg(p + i);
+        m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    }
+    wnorm[w] = m;
 }
 
 // ---- heap helpers: min-heap on (score asc, id desc) so the root is the WORST kept candidate ----
@@ -190,7 +212,8 @@ __device__ __noinline__ float heap_push(float *heap_s, int *heap_i, int u, float
 template <int D>
 __global__ void __launch_bounds__(kThreads, 1)
 score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ users, int64_t nu,
-                    const __nv_bfloat16 *__restrict__ Bt, int64_t n_items, int n_tiles,
+                    const __nv_bfloat16 *__restrict__ Bt, const float *__restrict__ vnorm,
+                    const float *__restrict__ wnorm, int64_t n_items, int n_tiles,
                     const int64_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_col,
                     float *__restrict__ cand_s, int32_t *__restrict__ cand_i, float *__restrict__ tau_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -277,10 +300,26 @@ score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ us
         float *hs = &sm.heap_s[g][0][0];
         int *hi = &sm.heap_i[g][0][0];
         float tau = -FLT_MAX;
+        // c_u = 1.05 * 2^-8 * |u|: key = s + c_u |v| bounds the exact score from above
+        float cu = 0.f;
+        if (q < nu) {
+            const float4 *fu4 = reinterpret_cast<const float4 *>(Fu + (size_t)users[q] * D);
+            float n2 = 0.f;
+#pragma unroll 4
+            for (int j = 0; j < D / 4; ++j) {
+                const float4 a = __ldg(fu4 + j);
+                n2 += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+            }
+            cu = 1.05f * 0.00390625f * sqrtf(n2) * 1.000001f;
+        }
+        const float4 *wn4 = reinterpret_cast<const float4 *>(wnorm);
+        float4 wn_next = g < n_tiles ? __ldg(wn4 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
         int64_t mb = 0, me = 0;
         if (mask_rowptr && q < nu) { mb = mask_rowptr[q]; me = mask_rowptr[q + 1]; }
         int next_masked = (mb < me) ? __ldg(mask_col + mb) : 0x7fffffff;
         for (int t = g; t < n_tiles; t += NB) {
+            const float4 wn_t = wn_next;                   // window norms of this tile, fetched a tile ahead
+            if (t + NB < n_tiles) wn_next = __ldg(wn4 + t + NB);
             mbar_wait(smem_u32(&sm.tfull[g]), ((t / NB) & 1));
             tc_fence_after();
             const int tile_item0 = t * NT;
@@ -319,10 +358,19 @@ score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ us
 #pragma unroll
                 for (int i = 0; i < 4; ++i) m4[i] = fmaxf(m8[2 * i], m8[2 * i + 1]);
                 const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-                if (mx > tau) {                               // rare once the heap has warmed up
+                const float wn = c == 0 ? wn_t.x : (c == 1 ? wn_t.y : (c == 2 ? wn_t.z : wn_t.w));
+                if (fmaf(cu, wn, mx) > tau) {                 // rare once the heap has warmed up
+                    const float4 *vn4 = reinterpret_cast<const float4 *>(vnorm + item0);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (v[i] > tau) tau = heap_push(hs, hi, u, v[i], item0 + i);
+                    for (int i4 = 0; i4 < 8; ++i4) {
+                        const float4 n = __ldg(vn4 + i4);
+                        const float key0 = fmaf(cu, n.x, v[4 * i4]), key1 = fmaf(cu, n.y, v[4 * i4 + 1]);
+                        const float key2 = fmaf(cu, n.z, v[4 * i4 + 2]), key3 = fmaf(cu, n.w, v[4 * i4 + 3]);
+                        if (key0 > tau) tau = heap_push(hs, hi, u, key0, item0 + 4 * i4);
+                        if (key1 > tau) tau = heap_push(hs, hi, u, key1, item0 + 4 * i4 + 1);
+                        if (key2 > tau) tau = heap_push(hs, hi, u, key2, item0 + 4 * i4 + 2);
+                        if (key3 > tau) tau = heap_push(hs, hi, u, key3, item0 + 4 * i4 + 3);
+                    }
                 }
             }
             tc_fence_before();
@@ -351,7 +399,7 @@ __global__ void __launch_bounds__(256)
 score_refine_kernel(const float *__restrict__ Fu, const float *__restrict__ Fi,
                     const int64_t *__restrict__ users, int64_t nu, int d,
                     const int32_t *__restrict__ cand_i, const float *__restrict__ tau,
-                    const unsigned int *__restrict__ vmax_bits, int k, int32_t *__restrict__ out_ids,
+                    int k, int32_t *__restrict__ out_ids,
                     float *__restrict__ out_scores, int32_t *__restrict__ fail) {
     const int lane = threadIdx.x & 31;
     const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -360,10 +408,6 @@ score_refine_kernel(const float *__restrict__ Fu, const float *__restrict__ Fi,
     constexpr int CPL = CAND / 32;                 // candidates per lane
     float sc[CPL];
     int id[CPL];
-    float un2 = 0.f;
-    for (int j = lane; j < d; j += 32) un2 += fu[j] * fu[j];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) un2 += __shfl_xor_sync(0xffffffffu, un2, off);
 #pragma unroll
     for (int h = 0; h < CPL; ++h) {
         id[h] = cand_i[q * CAND + lane + 32 * h];
@@ -409,14 +453,12 @@ score_refine_kernel(const float *__restrict__ Fu, const float *__restrict__ Fi,
         kth = bs;
     }
     if (lane == 0) {
-        // |bf16(u).bf16(v) - u.v| <= (2^-8 + 2^-16) |u||v| ; anything the filter dropped has an
-        // exact score <= tau + eps.  The k-th exact score must clear that bound.
-        const float vmax = __uint_as_float(*vmax_bits);
-        const float eps = 1.05f * 0.00390625f * sqrtf(un2) * vmax;
+        // every item the filter dropped has exact score <= key <= its group's threshold (the keys
+        // are upper bounds of the exact scores): the k-th exact score must clear the largest one.
         float tq = tau[q * NB];
 #pragma unroll
         for (int g = 1; g < NB; ++g) tq = fmaxf(tq, tau[q * NB + g]);
-        fail[q] = (kth > tq + eps) ? 0 : 1;
+        fail[q] = (kth > tq) ? 0 : 1;
     }
 }
 
@@ -426,7 +468,7 @@ score_refine_kernel(const float *__restrict__ Fu, const float *__restrict__ Fi,
 // ---- C ABI ---------------------------------------------------------------------------------
 namespace {
 struct TcLayout {
-    size_t bt, vmax, cand_s, cand_i, tau, total;
+    size_t bt, vnorm, wnorm, cand_s, cand_i, tau, total;
 };
 TcLayout tc_layout(int64_t nu, int64_t n_items, int32_t d) {
     using namespace lgcn::tc;
@@ -434,8 +476,9 @@ TcLayout tc_layout(int64_t nu, int64_t n_items, int32_t d) {
     TcLayout L;
     const int64_t n_pad = (n_items + NT - 1) / NT * NT;
     L.bt = 0;                                           // prepared item tiles (independent of nu)
-    L.vmax = up(L.bt + (size_t)n_pad * d * 2);          // max item norm (independent of nu)
-    L.cand_s = L.vmax + 256;
+    L.vnorm = up(L.bt + (size_t)n_pad * d * 2);         // item norms (independent of nu)
+    L.wnorm = up(L.vnorm + (size_t)n_pad * 4);          // largest norm per 32-item window
+    L.cand_s = up(L.wnorm + (size_t)(n_pad / 32) * 4);
     L.cand_i = up(L.cand_s + (size_t)nu * CAND * 4);
     L.tau = up(L.cand_i + (size_t)nu * CAND * 4);
     L.total = up(L.tau + (size_t)nu * 4 * lgcn::tc::NB);
@@ -459,13 +502,15 @@ extern "C" int lgcn_score_tc_prepare(const float *Fi, int64_t n_items, int32_t d
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
     const int64_t n_pad = (n_items + NT - 1) / NT * NT;
-    unsigned int *vmax = reinterpret_cast<unsigned int *>(ws + L.vmax);
-    cudaError_t e = cudaMemsetAsync(vmax, 0, 4, st);
-    if (e != cudaSuccess) return (int)e;
+    float *vnorm = reinterpret_cast<float *>(ws + L.vnorm);
+    float *wnorm = reinterpret_cast<float *>(ws + L.wnorm);
     const int64_t threads = n_pad * (d / 8);
     const unsigned grid = (unsigned)((threads + 255) / 256);
-    if (d == 64) prepare_items_kernel<64><<<grid, 256, 0, st>>>(Fi, n_items, n_pad, reinterpret_cast<__nv_bfloat16 *>(ws + L.bt), vmax);
-    else prepare_items_kernel<128><<<grid, 256, 0, st>>>(Fi, n_items, n_pad, reinterpret_cast<__nv_bfloat16 *>(ws + L.bt), vmax);
+    if (d == 64) prepare_items_kernel<64><<<grid, 256, 0, st>>>(Fi, n_items, n_pad, reinterpret_cast<__nv_bfloat16 *>(ws + L.bt), vnorm);
+    else prepare_items_kernel<128><<<grid, 256, 0, st>>>(Fi, n_items, n_pad, reinterpret_cast<__nv_bfloat16 *>(ws + L.bt), vnorm);
+    LGCN_LAUNCH_CHECK();
+    const int64_t n_windows = n_pad / 32;
+    window_norm_kernel<<<(unsigned)((n_windows + 255) / 256), 256, 0, st>>>(vnorm, n_windows, wnorm);
     LGCN_LAUNCH_CHECK();
     return 0;
 }
@@ -489,7 +534,8 @@ extern "C" int lgcn_score_tc_topk(const float *Fu, const float *Fi, const int64_
     float *cand_s = reinterpret_cast<float *>(ws + L.cand_s);
     int32_t *cand_i = reinterpret_cast<int32_t *>(ws + L.cand_i);
     float *tau = reinterpret_cast<float *>(ws + L.tau);
-    const unsigned int *vmax = reinterpret_cast<const unsigned int *>(ws + L.vmax);
+    const float *vnorm = reinterpret_cast<const float *>(ws + L.vnorm);
+    const float *wnorm = reinterpret_cast<const float *>(ws + L.wnorm);
     const int n_tiles = (int)((n_items + NT - 1) / NT);
     const unsigned grid = (unsigned)((nu + MT - 1) / MT);
     if (d == 64) {
@@ -499,7 +545,7 @@ extern "C" int lgcn_score_tc_topk(const float *Fu, const float *Fi, const int64_
             if (e != cudaSuccess) return (int)e;
             done = true;
         }
-        score_filter_kernel<64><<<grid, kThreads, sizeof(FilterSmem<64>), st>>>(Fu, users, nu, Bt, n_items, n_tiles, mask_rowptr, mask_col, cand_s, cand_i, tau);
+        score_filter_kernel<64><<<grid, kThreads, sizeof(FilterSmem<64>), st>>>(Fu, users, nu, Bt, vnorm, wnorm, n_items, n_tiles, mask_rowptr, mask_col, cand_s, cand_i, tau);
     } else {
         static bool done = false;
         if (!done) {
@@ -507,11 +553,11 @@ extern "C" int lgcn_score_tc_topk(const float *Fu, const float *Fi, const int64_
             if (e != cudaSuccess) return (int)e;
             done = true;
         }
-        score_filter_kernel<128><<<grid, kThreads, sizeof(FilterSmem<128>), st>>>(Fu, users, nu, Bt, n_items, n_tiles, mask_rowptr, mask_col, cand_s, cand_i, tau);
+        score_filter_kernel<128><<<grid, kThreads, sizeof(FilterSmem<128>), st>>>(Fu, users, nu, Bt, vnorm, wnorm, n_items, n_tiles, mask_rowptr, mask_col, cand_s, cand_i, tau);
     }
     LGCN_LAUNCH_CHECK();
     const unsigned rgrid = (unsigned)((nu * 32 + 255) / 256);
-    score_refine_kernel<<<rgrid, 256, 0, st>>>(Fu, Fi, users, nu, d, cand_i, tau, vmax, k, out_ids, out_scores, fail);
+    score_refine_kernel<<<rgrid, 256, 0, st>>>(Fu, Fi, users, nu, d, cand_i, tau, k, out_ids, out_scores, fail);
     LGCN_LAUNCH_CHECK();
     return 0;
 }
