@@ -212,7 +212,19 @@ def run_b200(args):
             d_local = d // world
             local = column_shard(table, rank, world)
             del table
-            eng = FeatureShardedEngine(csr, U, I, B, K, local, batch_size=BS)
+            fusion = None
+            if args.fusion:            # item block projected item-sharded: this rank's content rows
+                c = 768
+                ipr = -(-I // world)
+                i0, i1 = min(I, rank * ipr), min(I, (rank + 1) * ipr)
+                gen_c = torch.Generator(device=dev).manual_seed(1000 + rank)
+                content = torch.randn((i1 - i0, c), device=dev, generator=gen_c)
+                gen_w = torch.Generator(device=dev).manual_seed(7)        # replicated W / b
+                bound = (6.0 / (d + c + d)) ** 0.5
+                W = torch.empty((d, d + c), device=dev).uniform_(-bound, bound, generator=gen_w)
+                bb = torch.empty((d,), device=dev).uniform_(-(d + c) ** -0.5, (d + c) ** -0.5, generator=gen_w)
+                fusion = dict(content=content, weight=W, bias=bb)
+            eng = FeatureShardedEngine(csr, U, I, B, K, local, batch_size=BS, fusion=fusion)
         else:
             eng = RowShardedEngine(csr, U, I, B, K, table, batch_size=BS)
             del table
@@ -379,7 +391,7 @@ def main():
     ap.add_argument("--workload", default="amazon", choices=sorted(CPU_SAMPLE))
     ap.add_argument("--fusion", action="store_true",
                     help="LightGCN_Fusion: 768-d side embeddings projected and merged into the item "
-                         "rows of layer 0 (BASELINE.json configs[3]); single GPU")
+                         "rows of layer 0 (BASELINE.json configs[3]); item-sharded on N > 1 GPUs")
     ap.add_argument("--eval-users", type=int, default=18944)
     ap.add_argument("--parallelism", default="feature", choices=["feature", "row"],
                     help="multi-GPU partitioning: feature columns (no propagation collectives) or "

@@ -141,6 +141,16 @@ class LightGCNEngine:
         ops.fusion_proj_fwd(self.P[U:U + I], f["C"], f["W"], f["b"], out=self.X0[U:U + I])
         return self.X0
 
+    def _fusion_backward(self, acc):
+        """Gradients of the fused item block from dL/dX0 (``acc``): fills ``g_eid`` (id
+        embeddings), ``gW`` and ``gb`` (autograd of reference ``models/lightgcn_fusion.py:45-49``)."""
+        U, I = self.U, self.I
+        f = self.fusion
+        f["gW"].zero_()
+        f["gb"].zero_()
+        ops.fusion_proj_bwd(self.P[U:U + I], f["C"], f["W"], self.X0[U:U + I], acc[U:U + I],
+                            g_eid=f["g_eid"], gW=f["gW"], gb=f["gb"])
+
     def propagate(self):
         """F = mean_k A^k E0 (reference ``models/lightgcn.py:44-54``); returns the [N,d] table."""
         return ops.propagate(self.g, self.layer0(), self.K, out=self.F, work=self.work)
@@ -180,10 +190,7 @@ class LightGCNEngine:
                           betas=self.betas, eps=self.eps)
         else:
             f = self.fusion
-            f["gW"].zero_()
-            f["gb"].zero_()
-            ops.fusion_proj_bwd(self.P[U:U + I], f["C"], f["W"], self.X0[U:U + I], acc[U:U + I],
-                                g_eid=f["g_eid"], gW=f["gW"], gb=f["gb"])
+            self._fusion_backward(acc)
             kw = dict(betas=self.betas, eps=self.eps)
             sc = self.adam_scalars
             ops.adam(self.P[:U], acc[:U], self.m[:U], self.v[:U], sc, g1=self.G2[:U], **kw)

@@ -58,6 +58,18 @@ def _worker(rank, world, port, q):
                                    orc._p(Y_loc), ctypes.c_int64(r1 - r0), ctypes.c_int32(d))
         Y_ref = orc.spmm(a["rowptr"], a["col"], a["val"], E0)
         assert np.array_equal(Y_loc, Y_ref[r0:r1])
+        # ---- fusion item block: column shards <-> full rows of the rank's item block ----------
+        from gcn_recommendation_b200.dist import cols_to_rows, rows_to_cols
+        Ei = torch.from_numpy(np.ascontiguousarray(E0[U:U + I]))            # [I, d], I odd-sized vs world
+        ipr = -(-I // world)
+        a_in, a_out = torch.zeros((world, ipr, dl)), torch.zeros((world, ipr, dl))
+        a2a = lambda o, i: dist.all_to_all_single(o, i)                    # noqa: E731
+        rows = cols_to_rows(Ei[:, rank * dl:(rank + 1) * dl].contiguous(), a_in, a_out,
+                            torch.zeros((ipr, d)), a2a)
+        i0, i1 = rank * ipr, min(I, (rank + 1) * ipr)
+        assert torch.equal(rows[:i1 - i0], Ei[i0:i1])
+        back = rows_to_cols(rows, a_in, a_out, torch.zeros((I, dl)), a2a)
+        assert torch.equal(back, Ei[:, rank * dl:(rank + 1) * dl])
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))

@@ -538,6 +538,85 @@ def test_feature_sharded_step_emulated_on_one_gpu(golden, dev):
     assert mx < 1e-3 and fro < 1e-5
 
 
+def test_feature_sharded_fusion_step_emulated_on_one_gpu(golden, dev):
+    """LightGCN_Fusion on the feature-sharded engine: two "ranks" run as threads on one GPU, the
+    all-to-all (column shards <-> item-block rows) and the all-reduces emulated in-process.  The
+    item block is projected item-sharded; the result must track the reference's loss curve and
+    final parameters, and W / b must stay bit-identical on both ranks."""
+    import threading
+    from gcn_recommendation_b200.dist import FeatureShardedEngine, column_shard
+    g = golden("tiny_fusion_d64_k3")
+    U, I, B, K = int(g["num_users"]), int(g["num_items"]), int(g["num_brands"]), int(g["K"])
+    csr = _graph(g, dev)
+    full = torch.cat([_t(g["init/user_embedding.weight"], dev), _t(g["init/item_id_embedding.weight"], dev),
+                      _t(g["init/brand_embedding.weight"], dev)]).contiguous()
+    C = _t(g["init/item_content_embedding"], dev)
+    world = 2
+    bar = threading.Barrier(world)
+    slots = [None] * world
+
+    def make_allreduce(r):
+        def ar(t):
+            slots[r] = t
+            bar.wait()
+            tot = slots[0] + slots[1]            # same order on both ranks -> bit-identical
+            bar.wait()
+            t.copy_(tot)
+            bar.wait()
+        return ar
+
+    def make_alltoall(r):
+        def a2a(out, inp):
+            slots[r] = inp
+            bar.wait()
+            for s in range(world):
+                out[s].copy_(slots[s][r])
+            bar.wait()
+        return a2a
+
+    ipr = -(-I // world)
+    engs = []
+    for r in range(world):
+        fus = dict(content=C[r * ipr:min(I, (r + 1) * ipr)].contiguous(),
+                   weight=_t(g["init/item_fusion_layer.weight"], dev),
+                   bias=_t(g["init/item_fusion_layer.bias"], dev), alltoall=make_alltoall(r))
+        engs.append(FeatureShardedEngine(csr, U, I, B, K, column_shard(full, r, world), world=world, rank=r,
+                                         allreduce=make_allreduce(r), fusion=fus, lr=float(g["lr"]),
+                                         weight_decay=float(g["lam"]), batch_size=int(g["bs"])))
+    losses = [[], []]
+    errs = []
+
+    def run(r):
+        try:
+            torch.cuda.set_device(dev)
+            for s in range(len(g["losses"])):
+                loss = engs[r].bpr_step(_t(g["batch_users"][s], dev, torch.int64),
+                                        _t(g["batch_pos"][s], dev, torch.int64),
+                                        _t(g["batch_neg"][s], dev, torch.int64), use_graph=False)
+                losses[r].append(loss.item())
+        except Exception as e:  # pragma: no cover
+            errs.append(repr(e))
+            bar.abort()
+
+    ths = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join(timeout=120)
+    assert not errs, errs
+    assert losses[0] == losses[1]
+    assert np.allclose(losses[0], g["losses"], rtol=2e-5, atol=0)
+    P = torch.cat([e.P for e in engs], dim=1).cpu().numpy()
+    ref = np.concatenate([g["final/user_embedding.weight"], g["final/item_id_embedding.weight"],
+                          g["final/brand_embedding.weight"]], 0)
+    mx, fro = rel_err(P, ref)
+    assert mx < 1e-3 and fro < 1e-5
+    assert torch.equal(engs[0].fusion["W"], engs[1].fusion["W"])
+    assert torch.equal(engs[0].fusion["b"], engs[1].fusion["b"])
+    mx, fro = rel_err(engs[0].fusion["W"].cpu().numpy(), g["final/item_fusion_layer.weight"])
+    assert mx < 1e-3 and fro < 1e-5
+
+
 # ---------------------------------------------------------------------------- f1 sampler
 def test_device_sampler_epoch_is_a_permutation_with_valid_negatives(dev):
     from gcn_recommendation_b200 import ops, synth
