@@ -291,7 +291,13 @@ def run_b200(args):
     for tag, a, b in prof:
         per_tag.setdefault(tag, []).append(a.elapsed_time(b))
     g_local = eng.g
-    extra = {"plain": 0, "add": 1, "mean": K, "adam": 7}
+    # extra table streams per mode; the backward addends g' / reg-grad have <= 3*batch
+    # non-zero rows and are skipped through row flags, so they are not counted as streams:
+    # add = A x + g' -> 0 extra; add_xf (first hop, x = g' sparse too) reads no X either;
+    # adam = p,m,v read + written -> 6 extra
+    extra = {"plain": 0, "add": 0, "add_xf": -1, "mean": K, "adam": 6}
+    if world > 1 and args.parallelism == "row":
+        extra.update(add=1, adam=7)                  # the row-sharded engine reads its addends densely
     kernels = {}
     for tag, v in per_tag.items():
         ms = float(np.mean(v))
@@ -304,7 +310,7 @@ def run_b200(args):
     tp = os.path.join(ROOT, "profiles", "spmm_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(f"{args.workload}:{dom}")
-    roofline = {"bound": "hbm", "kernel": f"spmm_chunk_kernel<{d_local},{dom}>",
+    roofline = {"bound": "hbm", "kernel": ops.spmm_kernel_name(g_local, d_local, dom),
                 "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_gb"] * 1e9,

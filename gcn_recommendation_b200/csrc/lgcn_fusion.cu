@@ -9,6 +9,13 @@
 // this HBM-bound is the next step for this kernel (DESIGN.md section "fusion_proj").
 #include "lgcn_common.cuh"
 
+extern "C" int lgcn_fusion_fwd_tc_try(const float *Eid, const float *C, const float *W, const float *b,
+                                      int64_t n_items, int32_t d, int32_t c, float *H, cudaStream_t st);
+extern "C" int lgcn_fusion_bwd_w_tc_try(const float *Eid, const float *C, const float *H, const float *gH,
+                                        int64_t n_items, int32_t d, int32_t c, float *gW, float *gb,
+                                        cudaStream_t st);
+static int g_fusion_force_simt = 0;
+
 namespace lgcn {
 
 constexpr int FM = 64;   // items per CTA tile
@@ -246,6 +253,10 @@ static int fusion_bwd_launch(const float *Eid, const float *C, const float *W, c
     const int64_t blocks = (n_items + FM - 1) / FM;
     fusion_bwd_eid_kernel<D><<<(unsigned)blocks, kFusThreads, 0, st>>>(W, H, gH, n_items, c, gEid);
     LGCN_LAUNCH_CHECK();
+    if (!g_fusion_force_simt) {             // tensor-core 3xTF32 path (lgcn_fusion_tc.cu)
+        const int rc = lgcn_fusion_bwd_w_tc_try(Eid, C, H, gH, n_items, D, c, gW, gb, st);
+        if (rc != -100) return rc;
+    }
     const int kin = D + c;
     const int ktiles = (kin + GW_KT - 1) / GW_KT;
     // enough CTAs to fill the chip a few times, few enough to keep the atomic traffic small
@@ -263,9 +274,6 @@ static int fusion_bwd_launch(const float *Eid, const float *C, const float *W, c
 
 }  // namespace lgcn
 
-extern "C" int lgcn_fusion_fwd_tc_try(const float *Eid, const float *C, const float *W, const float *b,
-                                      int64_t n_items, int32_t d, int32_t c, float *H, cudaStream_t st);
-static int g_fusion_force_simt = 0;
 // test hook: 1 = always use the fp32 SIMT kernels (the tensor-core path is the default)
 extern "C" LGCN_API void lgcn_fusion_force_simt(int on) { g_fusion_force_simt = on; }
 

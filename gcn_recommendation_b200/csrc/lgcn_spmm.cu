@@ -143,10 +143,12 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
 #pragma unroll
                 for (int i = 0; i < B; ++i)
                     if (on[i]) {
-                        // all-zero addend rows (no gradient landed there) are read from the
-                        // cache-resident zero row instead of HBM
+                        // all-zero addend rows (no gradient landed there) are not read at all
+                        // (redirecting them to one zero row made every SM hammer the same L2
+                        // line with no-allocate loads: 7.0 ms vs 6.1 ms dense at the Amazon shape)
                         const bool nz = ((rfw[(rb + i) >> 2] >> (((rb + i) & 3) * 8)) & 0xffu) != 0;
-                        t[i] = ld_s<HINT>(nz ? a.addend + off[i] : a.zero_row + coff, pol);
+                        t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (nz) t[i] = ld_s<HINT>(a.addend + off[i], pol);
                     }
 #pragma unroll
                 for (int i = 0; i < B; ++i)
@@ -180,8 +182,9 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
                 for (int i = 0; i < B; ++i)
                     if (on[i]) {
                         const bool nz = ((rfw[(rb + i) >> 2] >> (((rb + i) & 3) * 8)) & 0xffu) != 0;
-                        if (a.addend) g[i] = ld_s<HINT>(nz ? a.addend + off[i] : a.zero_row + coff, pol);
-                        if (a.addend2) g2[i] = ld_s<HINT>(nz ? a.addend2 + off[i] : a.zero_row + coff, pol);
+                        g[i] = g2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (a.addend && nz) g[i] = ld_s<HINT>(a.addend + off[i], pol);
+                        if (a.addend2 && nz) g2[i] = ld_s<HINT>(a.addend2 + off[i], pol);
                         p[i] = ld_s<HINT>(a.p + off[i], pol);
                         m[i] = ld_s<HINT>(a.m + off[i], pol);
                         vv[i] = ld_s<HINT>(a.v + off[i], pol);

@@ -180,14 +180,13 @@ class LightGCNEngine:
         hops = K - 1 if nofus else K
         rf, zr = self.rowflag, self.zero_row
         for k in range(hops):
-            # hop 0 gathers g' itself (<= 3*batch non-zero rows): flagged gathers
-            # (skipping the all-zero ADDEND rows the same way was measured neutral-to-slower:
-            # the addend is a perfectly coalesced stream, so it is read densely)
+            # hop 0 gathers g' itself (<= 3*batch non-zero rows): flagged gathers.  The addend of
+            # every hop is g' too: its all-zero rows are not read (1 ms per hop at the Amazon shape)
             acc = ops.spmm(g, acc, out=self.work[k % 2] if K > 1 else self.F, addend=self.G1,
-                           x_rowflag=rf if k == 0 else None, zero_row=zr)
+                           x_rowflag=rf if k == 0 else None, addend_rowflag=rf, zero_row=zr)
         if nofus:
             ops.spmm_adam(g, acc, self.P, self.m, self.v, self.adam_scalars, addend=self.G2,
-                          betas=self.betas, eps=self.eps)
+                          betas=self.betas, eps=self.eps, addend_rowflag=rf, zero_row=zr)
         else:
             f = self.fusion
             self._fusion_backward(acc)

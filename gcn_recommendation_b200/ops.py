@@ -54,6 +54,19 @@ def _spmm_args(g, x, mode, d):
     return a
 
 
+def spmm_kernel_name(g, d, mode):
+    """Name of the kernel ``lgcn_spmm`` picks for this graph / width / mode (mirrors the selection
+    in csrc/lgcn_spmm.cu ``launch_mode``; used by bench.py to label the roofline)."""
+    lanes = min(32, d // 4)
+    groups = 32 // lanes
+    rbig = min(lanes, max(4, 2048 // d))
+    if (g.n_rows // rbig) < 148 * 32 * groups:
+        return f"spmm_chunk_kernel<{d},{mode},4-row chunks>"
+    if mode in ("adam", "add_xf"):
+        return f"spmm_chunk_kernel<{d},{mode}>"
+    return f"spmm_ring_kernel<{d},{mode}>"
+
+
 def _check_table(t, rows, d, name):
     if t.dim() != 2 or t.shape[0] < rows or t.shape[1] != d:
         raise _lib.LgcnError(f"{name}: expected at least [{rows},{d}], got {tuple(t.shape)}")
@@ -89,7 +102,7 @@ def spmm(g, x, out=None, addend=None, mean_layers=None, x_rowflag=None, addend_r
     else:
         a = _spmm_args(g, x, SPMM_PLAIN, d)
     a.y = ptr(out)
-    _launch_spmm(a, g, x.device, ("plain", "add", "mean")[a.mode])
+    _launch_spmm(a, g, x.device, "add_xf" if x_rowflag is not None else ("plain", "add", "mean")[a.mode])
     return out
 
 

@@ -48,5 +48,9 @@ print(f"tc vs simt max rel err {err:.2e}")
 gE = torch.empty((n, d), device=dev)
 gW = torch.zeros((d, d + c), device=dev)
 gb = torch.zeros((d,), device=dev)
-ms = timeit(lambda: ops.fusion_proj_bwd(E, C, W, H, gH, g_eid=gE, gW=gW, gb=gb))
-print(f"bwd n={n} d={d}: {ms:.2f} ms  {(flops + 2.0 * n * d * d) / ms / 1e9:.1f} TFLOP/s")
+for simt in (0, 1):
+    lib.lgcn_fusion_force_simt(simt)
+    ms = timeit(lambda: ops.fusion_proj_bwd(E, C, W, H, gH, g_eid=gE, gW=gW, gb=gb))
+    print(f"bwd {'simt' if simt else 'tc  '} (gE_id + gW + gb) n={n} d={d}: {ms:.2f} ms  "
+          f"{(flops + 2.0 * n * d * d) / ms / 1e9:.1f} TFLOP/s (fp32-equivalent)")
+lib.lgcn_fusion_force_simt(0)

@@ -28,6 +28,13 @@ N = U + I + B
 x = torch.randn((N, d), device=dev)
 y = torch.empty_like(x)
 add = torch.randn((N, d), device=dev) if mode != "plain" else None
+if mode == "addflag":     # a later Horner hop: dense x, addend g' with 3*2048 non-zero rows, flagged
+    rows = torch.randint(0, N, (6144,), device=dev)
+    add.zero_()
+    add[rows] = torch.randn((6144, d), device=dev)
+    flag = torch.zeros(N + 32, dtype=torch.uint8, device=dev)
+    flag[rows] = 1
+    zero_row = torch.zeros(256, device=dev)
 if mode == "hop1":        # the first Horner hop: x = g' has 3*2048 non-zero rows, flagged
     rows = torch.randint(0, N, (6144,), device=dev)
     x.zero_()
@@ -44,6 +51,8 @@ for i in range(n):
         ops.spmm(g, x, out=y)
     elif mode == "add":
         ops.spmm(g, x, out=y, addend=add)
+    elif mode == "addflag":
+        ops.spmm(g, x, out=y, addend=add, addend_rowflag=flag, zero_row=zero_row)
     elif mode == "hop1":
         ops.spmm(g, x, out=y, addend=add, x_rowflag=flag, addend_rowflag=flag, zero_row=zero_row)
     elif mode == "mean":
