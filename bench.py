@@ -295,7 +295,8 @@ def run_b200(args):
     # non-zero rows and are skipped through row flags, so they are not counted as streams:
     # add = A x + g' -> 0 extra; add_xf (first hop, x = g' sparse too) reads no X either;
     # adam = p,m,v read + written -> 6 extra
-    extra = {"plain": 0, "add": 0, "add_xf": -1, "mean": K, "adam": 6}
+    # add_xs (first hop: sparse x, only the non-zero output rows written) streams the entries only
+    extra = {"plain": 0, "add": 0, "add_xf": -1, "add_xs": -2, "mean": K, "adam": 6}
     if world > 1 and args.parallelism == "row":
         extra.update(add=1, adam=7)                  # the row-sharded engine reads its addends densely
     kernels = {}

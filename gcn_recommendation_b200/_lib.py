@@ -19,9 +19,10 @@ SPMM_PLAIN, SPMM_ADD, SPMM_MEAN, SPMM_ADAM = 0, 1, 2, 3
 SPMM_F_STREAM_HINTS = 1
 SPMM_F_NO_RING = 2
 SPMM_F_BIG_PATH = 4
+SPMM_F_COLD_FIRST = 8
 SPMM_F_FORCE_RING = 16
 BPR_GP_INCLUDES_GF, BPR_NO_GRAD = 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class SpmmArgs(ctypes.Structure):
@@ -35,6 +36,7 @@ class SpmmArgs(ctypes.Structure):
         ("addend2", c_vp), ("p", c_vp), ("m", c_vp), ("v", c_vp), ("adam_scalars", c_vp),
         ("beta1", c_f32), ("beta2", c_f32), ("eps", c_f32), ("g_out", c_vp),
         ("flags", c_i32), ("x_rowflag", c_vp), ("addend_rowflag", c_vp), ("zero_row", c_vp),
+        ("y_rowflag", c_vp),
     ]
 
 

@@ -69,6 +69,28 @@ __device__ __forceinline__ int2 ld_cv(const int2 *p, uint64_t pol) {
     return HINT ? ld_stream_i2_hint(p, pol) : __ldg(p);
 }
 
+// Column classes of the graph plan (include/lgcn.h: bits 31/30 of lgcn_colval.col).  A gathered
+// row of a HOT column (one of the highest-degree nodes, as many as fit the L2 budget) is kept with
+// evict_last, the row of a column referenced once in the whole launch leaves L2 first, the rest
+// is evict_normal (or evict_first with LGCN_SPMM_F_COLD_FIRST: reuse distances of mid-degree
+// columns are far beyond L2 at the Amazon shape).
+struct GatherPolicy {
+    uint64_t last, mid, first;
+};
+template <bool HINT>
+__device__ __forceinline__ GatherPolicy gather_policy(int flags, uint64_t pol_first) {
+    GatherPolicy g{0ull, 0ull, 0ull};
+    if (HINT) {
+        g.first = pol_first;
+        g.last = policy_evict_last();
+        g.mid = (flags & LGCN_SPMM_F_COLD_FIRST) ? pol_first : policy_evict_normal();
+    }
+    return g;
+}
+__device__ __forceinline__ uint64_t pick_policy(const GatherPolicy &g, int col_raw) {
+    return col_raw < 0 ? g.last : ((col_raw & LGCN_COL_ONCE) ? g.first : g.mid);
+}
+
 // ---- epilogue for one row held in registers (long-row combine path) -----------------------
 template <int D, int MODE>
 __device__ __forceinline__ void epilogue_row(const lgcn_spmm_args &a, int64_t row,
@@ -114,7 +136,7 @@ __device__ __forceinline__ void epilogue_row(const lgcn_spmm_args &a, int64_t ro
 template <int D, int MODE, int R, bool HINT>
 __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const float *stage,
                                                int64_t r0, int nvr, unsigned long_bits, uint64_t pol,
-                                               const unsigned (&rfw)[R / 4]) {
+                                               const unsigned (&rfw)[R / 4], unsigned wmask = 0xffffffffu) {
     using G = RowGeom<D>;
     const int sub = (threadIdx.x & 31) % G::LANES;
     constexpr int B = (MODE == LGCN_SPMM_ADAM || MODE == LGCN_SPMM_MEAN) ? 2 : 4;  // rows per batch
@@ -131,7 +153,7 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
 #pragma unroll
             for (int i = 0; i < B; ++i) {
                 const int rr = rb + i;
-                on[i] = rr < nvr && !((long_bits >> rr) & 1u);
+                on[i] = rr < nvr && !((long_bits >> rr) & 1u) && ((wmask >> rr) & 1u);
                 off[i] = (size_t)(r0 + rr) * D + coff;
             }
             if (MODE == LGCN_SPMM_PLAIN) {
@@ -206,6 +228,23 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
     }
 }
 
+// Sparse output of a flagged hop (lgcn_spmm_args.y_rowflag): a row is written only if it summed a
+// flagged row of x (bit in `touched`) or has a flagged addend; y_rowflag tells the consumer (the
+// next hop's x_rowflag) which rows exist.  Long rows are always written, densely, by the combine
+// kernel.  Returns the mask of the chunk's rows to write.
+template <int R>
+__device__ __forceinline__ unsigned sparse_out_mask(const lgcn_spmm_args &a, const unsigned (&rfw)[R / 4],
+                                                    unsigned touched, int64_t r0, int sub, int nvr,
+                                                    bool my_long) {
+    if (!a.y_rowflag) return 0xffffffffu;
+    unsigned wmask = touched;
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr)
+        if ((rfw[rr >> 2] >> ((rr & 3) * 8)) & 0xffu) wmask |= 1u << rr;
+    if (sub < nvr) a.y_rowflag[r0 + sub] = (uint8_t)(((wmask >> sub) & 1u) | (my_long ? 1u : 0u));
+    return wmask;
+}
+
 // ---- main kernel: one worker per chunk of R rows ---------------------------------------------
 template <int D, int MODE, int RSEL, bool HINT, bool XF>
 __global__ void __launch_bounds__(kThreads, (MODE == LGCN_SPMM_PLAIN || MODE == LGCN_SPMM_ADD) ? LGCN_SPMM_MINBLOCKS_LIGHT : LGCN_SPMM_MINBLOCKS)
@@ -213,6 +252,7 @@ spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
     using G = RowGeom<D>;
     using C = ChunkCfg<D, RSEL>;
     const uint64_t pol = HINT ? policy_evict_first() : 0ull;
+    const GatherPolicy gpol = gather_policy<HINT && !XF>(a.flags, pol);
     extern __shared__ __align__(16) float stage_all[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -270,10 +310,14 @@ spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
     // shows ~32 KB in flight per SM already saturates HBM for 512-byte random rows.)
     constexpr int U = C::U;
     float4 x[U][G::VEC];
+    bool xlive[U];                                        // XF: gather u of the batch read a flagged row
+    unsigned touched = 0;                                 // XF: rows of the chunk that summed one
 #pragma unroll
-    for (int u = 0; u < U; ++u)
+    for (int u = 0; u < U; ++u) {
+        xlive[u] = true;
 #pragma unroll
         for (int v = 0; v < G::VEC; ++v) x[u][v] = zero4;
+    }
 
     for (int t = 0; t < max_n; t += G::LANES) {
         int2 cvn = make_int2(0, 0);
@@ -289,11 +333,18 @@ spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
                 // redirected to the cache-resident zero row; all flag loads of the batch first
                 int cjs[U];
                 unsigned xfl[U];
+                bool live = false;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    cjs[u] = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
+                    cjs[u] = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES) & LGCN_COL_MASK;
                     xfl[u] = (unsigned)__ldg(a.x_rowflag + cjs[u]);
+                    live |= xfl[u] != 0 && j + u < cnt;
+                    xlive[u] = xfl[u] != 0;
                 }
+                // no flagged row among the batch's gathers (the common case while the gradient
+                // is still sparse): nothing to add -- rows that never see a live batch are zero
+                // filled (or, with y_rowflag, reported as all-zero and not written at all)
+                if (!__any_sync(0xffffffffu, live)) continue;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const float *src = xfl[u] ? a.x + (size_t)cjs[u] * D + sub * 4 : a.zero_row + sub * 4;
@@ -303,10 +354,16 @@ spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
             } else {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int cj = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
-                    const float *src = a.x + (size_t)cj * D + sub * 4;
+                    const int cr = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
+                    const float *src = a.x + (size_t)(cr & LGCN_COL_MASK) * D + sub * 4;
+                    if (HINT) {
+                        const uint64_t gp = pick_policy(gpol, cr);
 #pragma unroll
-                    for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
+                        for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4_hint(src + v * G::LANES * 4, gp);
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
+                    }
                 }
             }
 #pragma unroll
@@ -329,6 +386,7 @@ spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
                                 st_f4(stage + r * D + sub * 4 + v * G::LANES * 4, zero4);
                         cur = row;
                     }
+                    if (XF && xlive[u]) touched |= 1u << row;
 #pragma unroll
                     for (int v = 0; v < G::VEC; ++v) fma4(acc[v], wj, x[u][v]);
                 }
@@ -345,7 +403,8 @@ spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
             for (int v = 0; v < G::VEC; ++v) st_f4(stage + r * D + sub * 4 + v * G::LANES * 4, zero4);
     }
     __syncwarp();
-    chunk_epilogue<D, MODE, C::R, HINT>(a, stage, r0, nvr, long_bits, pol, rfw);
+    const unsigned wmask = XF ? sparse_out_mask<C::R>(a, rfw, touched, r0, sub, nvr, my_long) : 0xffffffffu;
+    chunk_epilogue<D, MODE, C::R, HINT>(a, stage, r0, nvr, long_bits, pol, rfw, wmask);
 }
 
 // compile-time unrolled loop: f(std::integral_constant<int, I>) for I in [0, N)
@@ -359,6 +418,10 @@ __device__ __forceinline__ void static_for(F &&f) {
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_hint(uint32_t dst, const void *src, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;"
+                 :: "r"(dst), "l"(src), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -399,6 +462,7 @@ spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
     using C = RingCfg<D>;
     constexpr int L = G::LANES, S = C::S;
     const uint64_t pol = HINT ? policy_evict_first() : 0ull;
+    const GatherPolicy gpol = gather_policy<HINT>(a.flags, pol);
     extern __shared__ __align__(16) float ring_smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -450,12 +514,18 @@ spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
     // lane of the shuffle, the tile register and the ring slot are all immediates).
     auto issue = [&](int t, auto jj_c) {
         constexpr int JJ = decltype(jj_c)::value;
-        const int cj = __shfl_sync(0xffffffffu, JJ < L ? cvA.x : cvB.x, JJ % L, L);
+        const int cr = __shfl_sync(0xffffffffu, JJ < L ? cvA.x : cvB.x, JJ % L, L);
         if (t + JJ < n_e) {
-            const char *src = xb + (uint64_t)(uint32_t)cj * (D * 4);
+            const char *src = xb + (uint64_t)(uint32_t)(cr & LGCN_COL_MASK) * (D * 4);
             const uint32_t dst = ring_s + (uint32_t)(JJ % S) * (D * 4);
+            if (HINT) {
+                const uint64_t gp = pick_policy(gpol, cr);
 #pragma unroll
-            for (int v = 0; v < G::VEC; ++v) cp_async16(dst + v * L * 16, src + v * L * 16);
+                for (int v = 0; v < G::VEC; ++v) cp_async16_hint(dst + v * L * 16, src + v * L * 16, gp);
+            } else {
+#pragma unroll
+                for (int v = 0; v < G::VEC; ++v) cp_async16(dst + v * L * 16, src + v * L * 16);
+            }
         }
         cp_async_commit();
     };
@@ -479,6 +549,7 @@ spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
             cp_async_wait<S - 1>();                       // this lane's bytes of entry e have landed
             const float wj = __int_as_float(__shfl_sync(0xffffffffu, cvA.y, J, L));
             const bool live = e < n_e;
+
             // leave every row that ends at or before e: the finished sum (zeros for the empty rows
             // that follow it) goes to the staging buffer, one row per trip
             while (G::GROUPS == 1 ? (e >= cur_end) : __any_sync(0xffffffffu, live && e >= cur_end)) {
@@ -518,6 +589,155 @@ spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
     }
     __syncwarp();
     chunk_epilogue<D, MODE, C::R, HINT>(a, stage, r0, nvr, long_bits, pol, rfw);
+}
+
+// ---- sparse-input hop: live-list kernel --------------------------------------------------------
+// Mode ADD with x_rowflag (the first two Horner hops: x = g' has <= 3*batch non-zero rows, its
+// first image ~15 % at the Amazon shape).  The dense ring kernel spends ~40 instructions on every
+// entry, which makes it ISSUE bound once the gathers are gone (ncu: 60 % issue-active, 2 % DRAM).
+// Here a worker (same chunks, staging and epilogue as the ring kernel) resolves the row flags of a
+// whole {col,val} tile at once -- one flag byte per lane, fetched a tile ahead -- ballots the LIVE
+// entries and walks only those: up to S gathers per batch into the smem slots (cp.async), the row
+// of a live entry found with one ballot over the per-lane row ends.  Dead entries cost nothing;
+// rows without a live entry are zero filled (or, with y_rowflag, reported and left unwritten).
+// The per-row sum is still a sequential fp32 FMA over the live entries in column order, and a
+// skipped entry would have added w * 0 = 0 exactly, so results stay bit-equal.
+template <int D, bool HINT>
+__global__ void __launch_bounds__(kRingWarps * 32)
+spmm_live_kernel(const __grid_constant__ lgcn_spmm_args a) {
+    using G = RowGeom<D>;
+    using C = RingCfg<D>;
+    constexpr int L = G::LANES, S = C::S;
+    const uint64_t pol = HINT ? policy_evict_first() : 0ull;
+    extern __shared__ __align__(16) float ring_smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int grp = lane / L;
+    const int sub = lane % L;
+    const int gshift = grp * L;
+    const unsigned gbits = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
+    float *stage = ring_smem + (size_t)((warp * G::GROUPS + grp) * (C::R + S)) * D;
+    const float *ring = stage + C::R * D + sub * 4;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+
+    const int64_t worker = ((int64_t)blockIdx.x * kRingWarps + warp) * G::GROUPS + grp;
+    const int64_t r0 = worker * C::R;
+    const int64_t left = a.n_rows - r0;
+    const int nvr = left <= 0 ? 0 : (left < C::R ? (int)left : C::R);
+
+    unsigned rfw[C::R / 4];
+#pragma unroll
+    for (int i = 0; i < C::R / 4; ++i)
+        rfw[i] = (a.addend_rowflag && nvr > 0)
+                     ? __ldg(reinterpret_cast<const unsigned *>(a.addend_rowflag + r0) + i) : 0xffffffffu;
+    unsigned rb = 0, re = 0;
+    if (sub < nvr) {
+        rb = __ldg(a.rowptr + r0 + sub);
+        re = __ldg(a.rowptr + r0 + sub + 1);
+    }
+    const bool my_long = (rb >> 31) != 0;
+    const int my_beg = (int)(rb & 0x7fffffffu);
+    int my_end = (int)(re & 0x7fffffffu);
+    int chunk_beg = __shfl_sync(0xffffffffu, my_beg, 0, L);
+    int chunk_end = __shfl_sync(0xffffffffu, my_end, nvr > 0 ? nvr - 1 : 0, L);
+    if (nvr == 0) chunk_beg = chunk_end = 0;
+    const unsigned long_bits = (__ballot_sync(0xffffffffu, my_long) >> gshift) & gbits;
+    my_end = sub < nvr ? my_end - chunk_beg : INT_MAX;   // relative to the chunk stream; sentinel
+
+    const int n_e = chunk_end - chunk_beg;
+    int max_n = n_e;
+#pragma unroll
+    for (int off = L; off < 32; off <<= 1)
+        max_n = max(max_n, __shfl_xor_sync(0xffffffffu, max_n, off));
+
+    const char *xb = reinterpret_cast<const char *>(a.x + sub * 4);
+    const int2 *cvp = reinterpret_cast<const int2 *>(a.colval) + chunk_beg;
+    const int2 z2 = make_int2(0, 0);
+    // tile pipeline: cvA = entries [t,t+L) with its flags resolved, cvB = [t+L,t+2L) with the flag
+    // load in flight, cvC = [t+2L,t+3L) in flight
+    int2 cvA = sub < n_e ? ld_cv<HINT>(cvp + sub, pol) : z2;
+    int2 cvB = L + sub < n_e ? ld_cv<HINT>(cvp + L + sub, pol) : z2;
+    int2 cvC = 2 * L + sub < n_e ? ld_cv<HINT>(cvp + 2 * L + sub, pol) : z2;
+    unsigned flA = __ldg(a.x_rowflag + (cvA.x & LGCN_COL_MASK));
+    unsigned flB = __ldg(a.x_rowflag + (cvB.x & LGCN_COL_MASK));
+
+    float4 acc[G::VEC];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int v = 0; v < G::VEC; ++v) acc[v] = zero4;
+    int cur = 0;                                          // row (within the chunk) being summed
+    unsigned touched = 0;                                 // rows that summed a live entry
+
+    for (int t = 0; t < max_n; t += L) {
+        const bool mine = t + sub < n_e && flA != 0;
+        unsigned lm = (__ballot_sync(0xffffffffu, mine) >> gshift) & gbits;    // live entries of the tile
+        while (__any_sync(0xffffffffu, lm != 0)) {
+            // up to S live entries: gathers first ...
+            unsigned m = lm;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const bool on = m != 0;
+                const int j = on ? __ffs(m) - 1 : 0;
+                m &= m - 1;
+                const int cj = __shfl_sync(0xffffffffu, cvA.x, j, L) & LGCN_COL_MASK;
+                if (on) {
+                    const char *src = xb + (uint64_t)(uint32_t)cj * (D * 4);
+                    const uint32_t dst = ring_s + (uint32_t)s * (D * 4);
+#pragma unroll
+                    for (int v = 0; v < G::VEC; ++v) cp_async16(dst + v * L * 16, src + v * L * 16);
+                }
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            // ... then their FMAs, in stream (= column) order
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const bool on = lm != 0;
+                const int j = on ? __ffs(lm) - 1 : 0;
+                lm &= lm - 1;
+                const float wj = __int_as_float(__shfl_sync(0xffffffffu, cvA.y, j, L));
+                const int e = t + j;
+                const unsigned passed = (__ballot_sync(0xffffffffu, my_end <= e) >> gshift) & gbits;
+                if (on) {
+                    const int row = __popc(passed);
+                    if (row != cur) {                     // flush the finished row, zero the skipped ones
+#pragma unroll
+                        for (int v = 0; v < G::VEC; ++v) {
+                            st_f4(stage + cur * D + sub * 4 + v * L * 4, acc[v]);
+                            acc[v] = zero4;
+                        }
+                        for (int r = cur + 1; r < row; ++r)
+#pragma unroll
+                            for (int v = 0; v < G::VEC; ++v)
+                                st_f4(stage + r * D + sub * 4 + v * L * 4, zero4);
+                        cur = row;
+                    }
+                    touched |= 1u << row;
+                    const float *slot = ring + s * D;
+#pragma unroll
+                    for (int v = 0; v < G::VEC; ++v) {
+                        const float4 xv = *reinterpret_cast<const float4 *>(slot + v * L * 4);
+                        fma4(acc[v], wj, xv);
+                    }
+                }
+            }
+        }
+        cvA = cvB;
+        flA = flB;
+        cvB = cvC;
+        flB = __ldg(a.x_rowflag + (cvB.x & LGCN_COL_MASK));
+        cvC = t + 3 * L + sub < n_e ? ld_cv<HINT>(cvp + t + 3 * L + sub, pol) : z2;
+    }
+    if (cur < nvr) {
+#pragma unroll
+        for (int v = 0; v < G::VEC; ++v) st_f4(stage + cur * D + sub * 4 + v * L * 4, acc[v]);
+        for (int r = cur + 1; r < nvr; ++r)
+#pragma unroll
+            for (int v = 0; v < G::VEC; ++v) st_f4(stage + r * D + sub * 4 + v * L * 4, zero4);
+    }
+    __syncwarp();
+    const unsigned wmask = sparse_out_mask<C::R>(a, rfw, touched, r0, sub, nvr, my_long);
+    chunk_epilogue<D, LGCN_SPMM_ADD, C::R, HINT>(a, stage, r0, nvr, long_bits, pol, rfw, wmask);
 }
 
 // ---- long rows: one worker per segment, partial sums to seg_ws -----------------------------
@@ -643,6 +863,23 @@ static int launch_chunks(const lgcn_spmm_args &a, cudaStream_t st) {
     return 0;
 }
 
+template <int D, bool HINT>
+static int launch_live(const lgcn_spmm_args &a, cudaStream_t st) {
+    using C = RingCfg<D>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(spmm_live_kernel<D, HINT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    const int64_t gb = (a.n_rows + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
+    if (gb > 0x7fffffffLL) return LGCN_E_TOO_LARGE;
+    spmm_live_kernel<D, HINT><<<(unsigned)gb, kRingWarps * 32, C::SMEM, st>>>(a);
+    LGCN_LAUNCH_CHECK();
+    return 0;
+}
+
 template <int D, int MODE, bool HINT>
 static int launch_ring(const lgcn_spmm_args &a, cudaStream_t st) {
     using C = RingCfg<D>;
@@ -676,12 +913,13 @@ static int launch_mode(const lgcn_spmm_args &a, cudaStream_t st) {
         const bool hint = (a.flags & LGCN_SPMM_F_STREAM_HINTS) != 0;
         int rc;
         const bool xf = MODE == LGCN_SPMM_ADD && a.x_rowflag != nullptr;
-        // Large graphs: the cp.async ring kernel.  ADAM (its epilogue wants the registers) and the
-        // flagged first hop (zero-filling ring slots was measured slower: 6.4 vs 5.0 ms) keep the
-        // register-batch chunk kernel.
-        const bool ring = !small && !xf && !(a.flags & LGCN_SPMM_F_NO_RING) &&
+        // Large graphs: the cp.async ring kernel; the flagged (sparse-input) hops run the live-list
+        // kernel.  ADAM (its epilogue wants the registers) keeps the register-batch chunk kernel.
+        const bool ring = !small && !(a.flags & LGCN_SPMM_F_NO_RING) &&
                           (MODE != LGCN_SPMM_ADAM || (a.flags & LGCN_SPMM_F_FORCE_RING));
-        if (ring) {
+        if (ring && xf) {
+            rc = hint ? launch_live<D, true>(a, st) : launch_live<D, false>(a, st);
+        } else if (ring) {
             rc = hint ? launch_ring<D, MODE, true>(a, st) : launch_ring<D, MODE, false>(a, st);
         } else if (xf) {        // sparse-input hop (first Horner hop): flagged gathers
             if (small) rc = launch_chunks<D, LGCN_SPMM_ADD, 1, false, true>(a, st);
@@ -736,6 +974,7 @@ extern "C" int lgcn_spmm(const lgcn_spmm_args *args, lgcn_stream_t stream) {
     if (a.n_long < 0) return LGCN_E_BAD_ARG;
     if ((a.x_rowflag || a.addend_rowflag) && !a.zero_row) return LGCN_E_BAD_ARG;
     if (a.x_rowflag && a.mode != LGCN_SPMM_ADD) return LGCN_E_BAD_ARG;
+    if (a.y_rowflag && !(a.x_rowflag && a.addend_rowflag)) return LGCN_E_BAD_ARG;
     if (a.n_long > 0 && (!a.long_row_ids || !a.long_rowptr || !a.long_colval || !a.long_seg_ptr ||
                          !a.seg_ws || a.seg_len <= 0 || a.n_seg <= 0))
         return LGCN_E_BAD_ARG;

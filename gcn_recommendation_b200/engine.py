@@ -15,6 +15,7 @@ one propagation, then fused score + mask + top-k and the hit / NDCG sums on the 
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -90,11 +91,16 @@ class LightGCNEngine:
         # 1 = row received a gradient this step (G1/G2 are zero elsewhere): lets the backward
         # hops skip the gathers / addend reads of all-zero rows
         self.rowflag = torch.zeros(self.N + 32, dtype=torch.uint8, device=self.dev)   # padded
+        # rows of the first hop's output that can be non-zero (written by the kernel): the second
+        # hop gathers only those, and the first hop does not write the others at all
+        self.rowflag2 = torch.zeros(self.N + 32, dtype=torch.uint8, device=self.dev)
         self.zero_row = torch.zeros(256, dtype=torch.float32, device=self.dev)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.adam_scalars = torch.zeros(2, dtype=torch.float32, device=self.dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self.bs = int(batch_size)
+        # False: dense first-hop output and dense second hop (A/B measurements, tests)
+        self.sparse_hops = os.environ.get("LGCN_SPARSE_HOPS", "1") != "0"
         self._alloc_batch(self.bs)
         self.fusion = None
         if fusion is not None:
@@ -179,11 +185,15 @@ class LightGCNEngine:
         acc = self.G1
         hops = K - 1 if nofus else K
         rf, zr = self.rowflag, self.zero_row
+        rf2 = self.rowflag2 if (self.sparse_hops and hops >= 2) else None
         for k in range(hops):
-            # hop 0 gathers g' itself (<= 3*batch non-zero rows): flagged gathers.  The addend of
-            # every hop is g' too: its all-zero rows are not read (1 ms per hop at the Amazon shape)
+            # hop 0 gathers g' itself (<= 3*batch non-zero rows): flagged gathers, and only the
+            # rows next to the batch's nodes are written (flags in rf2); hop 1 gathers under rf2
+            # (still ~80 % zero rows at the Amazon shape).  The addend of every hop is g' too: its
+            # all-zero rows are not read (1 ms per hop at the Amazon shape)
             acc = ops.spmm(g, acc, out=self.work[k % 2] if K > 1 else self.F, addend=self.G1,
-                           x_rowflag=rf if k == 0 else None, addend_rowflag=rf, zero_row=zr)
+                           x_rowflag=rf if k == 0 else (rf2 if k == 1 else None), addend_rowflag=rf,
+                           zero_row=zr, y_rowflag=rf2 if k == 0 else None)
         if nofus:
             ops.spmm_adam(g, acc, self.P, self.m, self.v, self.adam_scalars, addend=self.G2,
                           betas=self.betas, eps=self.eps, addend_rowflag=rf, zero_row=zr)

@@ -95,6 +95,35 @@ class NormAdjCSR:
         self.long_rowptr = torch.from_numpy(long_rp).to(dev)
         self.long_seg_ptr = torch.from_numpy(seg_ptr).to(dev)
 
+    # ---- L2 residency classes of the gathered columns (include/lgcn.h, LGCN_COL_*) ----------
+    def mark_hot_columns(self, n_hot, col_degree=None):
+        """Classify the columns of the short-row entries for the kernels' per-gather L2 policy:
+        the ``n_hot`` highest-degree nodes become HOT (bit 31 of ``colval[:,0]``: gathered rows
+        kept with evict_last), nodes of degree 1 -- gathered once per launch -- ONCE (bit 30:
+        evict_first).  The indices themselves (low 30 bits) are untouched; ``n_hot == 0`` clears
+        the classes.  Pure device integer work on the plan, done once per (graph, table width)."""
+        n_hot = max(0, min(int(n_hot), self.n_cols))
+        if getattr(self, "n_hot", 0) == n_hot and (n_hot == 0 or col_degree is None):
+            return
+        if self.n_cols > (1 << 30):
+            raise ValueError("column classes need n_cols <= 2^30")
+        if col_degree is None:
+            col_degree = getattr(self, "col_degree", None)
+        if col_degree is None:
+            if self.n_rows != self.n_cols:
+                raise ValueError("a row shard needs the column degrees of the whole graph")
+            col_degree = (self.rowptr[1:] - self.rowptr[:-1])        # symmetric: column = row degree
+        self.col_degree = col_degree
+        cls_bits = torch.zeros(self.n_cols, dtype=torch.int32, device=self.device)
+        if n_hot > 0:
+            cls_bits[col_degree == 1] = 0x40000000
+            hot = torch.topk(col_degree, n_hot, sorted=False).indices
+            hot = hot[col_degree[hot] > 1]
+            cls_bits[hot] = -0x80000000
+        cols = self.colval[:, 0] & 0x3fffffff
+        self.colval[:, 0] = cols | cls_bits[cols.long()]
+        self.n_hot = n_hot
+
     def seg_ws(self, d):
         if self.n_seg == 0:
             return None
@@ -249,9 +278,12 @@ class NormAdjCSR:
         """CSR of rows [row_begin, row_end) (columns stay global) for row-sharded propagation."""
         rp = self.rowptr[row_begin:row_end + 1]
         e0, e1 = int(rp[0].item()), int(rp[-1].item())
-        return NormAdjCSR((rp - e0).contiguous(), self.col[e0:e1].contiguous(),
-                          self.val[e0:e1].contiguous(), self.n_cols, row_begin=row_begin,
-                          long_row_threshold=self.long_row_threshold or 0, seg_len=self.seg_len)
+        g = NormAdjCSR((rp - e0).contiguous(), self.col[e0:e1].contiguous(),
+                       self.val[e0:e1].contiguous(), self.n_cols, row_begin=row_begin,
+                       long_row_threshold=self.long_row_threshold or 0, seg_len=self.seg_len)
+        if self.n_rows == self.n_cols:
+            g.col_degree = self.rowptr[1:] - self.rowptr[:-1]
+        return g
 
 
 _COO_CACHE = {}

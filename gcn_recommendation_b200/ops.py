@@ -6,6 +6,7 @@ Everything here launches hand-written sm_100a kernels; there is no eager/PyTorch
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -19,7 +20,10 @@ from ._lib import SPMM_ADAM, SPMM_ADD, SPMM_MEAN, SPMM_PLAIN, SpmmArgs, check, p
 COUNTERS = {"launches": 0}
 L2_STREAM_BYTES = 96 << 20      # tables larger than this are streamed with L2 evict_first hints
 PROFILE = None
-SPMM_FLAGS_EXTRA = 0           # OR-ed into lgcn_spmm_args.flags (tests / A-B measurements force a kernel)
+# L2 budget for the gathered rows of the highest-degree columns (kept with evict_last; the rows of
+# degree-1 columns leave first): LGCN_HOT_MB=0 turns the column classes off.
+HOT_BYTES = int(float(os.environ.get("LGCN_HOT_MB", "64")) * (1 << 20))
+SPMM_FLAGS_EXTRA = int(os.environ.get("LGCN_SPMM_FLAGS", "0"))           # OR-ed into lgcn_spmm_args.flags (tests / A-B measurements force a kernel)
 
 
 def _launch_spmm(a, g, dev, tag):
@@ -43,6 +47,10 @@ def _spmm_args(g, x, mode, d):
     a.flags = SPMM_FLAGS_EXTRA
     if g.n_cols * d * 4 > L2_STREAM_BYTES:
         a.flags |= _lib.SPMM_F_STREAM_HINTS
+    if a.flags & _lib.SPMM_F_STREAM_HINTS:
+        n_hot = HOT_BYTES // (4 * d)
+        if getattr(g, "n_hot", 0) != n_hot and (g.n_rows == g.n_cols or hasattr(g, "col_degree")):
+            g.mark_hot_columns(n_hot)
     if g.n_long > 0:
         a.n_long = g.n_long
         a.long_row_ids = ptr(g.long_row_ids, "i32")
@@ -62,7 +70,7 @@ def spmm_kernel_name(g, d, mode):
     rbig = min(lanes, max(4, 2048 // d))
     if (g.n_rows // rbig) < 148 * 32 * groups:
         return f"spmm_chunk_kernel<{d},{mode},4-row chunks>"
-    if mode in ("adam", "add_xf"):
+    if mode == "adam":
         return f"spmm_chunk_kernel<{d},{mode}>"
     return f"spmm_ring_kernel<{d},{mode}>"
 
@@ -73,9 +81,14 @@ def _check_table(t, rows, d, name):
 
 
 def spmm(g, x, out=None, addend=None, mean_layers=None, x_rowflag=None, addend_rowflag=None,
-         zero_row=None):
+         zero_row=None, y_rowflag=None):
     """out = A_hat x  (+ addend)  |  mean over [*mean_layers, A_hat x] (reference
-    ``models/lightgcn.py:45,54``).  ``g``: :class:`graph.NormAdjCSR`; ``x`` [n_cols, d]."""
+    ``models/lightgcn.py:45,54``).  ``g``: :class:`graph.NormAdjCSR`; ``x`` [n_cols, d].
+
+    Sparse-gradient shortcuts of the backward hops (include/lgcn.h): ``x_rowflag`` /
+    ``addend_rowflag`` mark the non-zero rows of ``x`` / ``addend``; with ``y_rowflag`` the kernel
+    reports which output rows can be non-zero and leaves the others UNWRITTEN (pass it as the
+    next hop's ``x_rowflag``)."""
     d = x.shape[1]
     _check_table(x, g.n_cols, d, "x")
     if out is None:
@@ -99,10 +112,17 @@ def spmm(g, x, out=None, addend=None, mean_layers=None, x_rowflag=None, addend_r
             a.x_rowflag = ptr(x_rowflag, "u8", allow_none=True)
             a.addend_rowflag = ptr(addend_rowflag, "u8", allow_none=True)
             a.zero_row = ptr(zero_row)
+            if y_rowflag is not None:
+                if y_rowflag.numel() < g.n_rows:
+                    raise _lib.LgcnError("y_rowflag: expected at least n_rows bytes")
+                a.y_rowflag = ptr(y_rowflag, "u8")
     else:
         a = _spmm_args(g, x, SPMM_PLAIN, d)
     a.y = ptr(out)
-    _launch_spmm(a, g, x.device, "add_xf" if x_rowflag is not None else ("plain", "add", "mean")[a.mode])
+    tag = ("plain", "add", "mean")[a.mode]
+    if x_rowflag is not None:
+        tag = "add_xs" if y_rowflag is not None else "add_xf"     # sparse in (+ sparse out)
+    _launch_spmm(a, g, x.device, tag)
     return out
 
 

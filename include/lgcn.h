@@ -33,7 +33,7 @@ typedef struct CUstream_st *lgcn_stream_t; /* == cudaStream_t */
 #define LGCN_API
 #endif
 
-#define LGCN_ABI_VERSION 3
+#define LGCN_ABI_VERSION 4
 
 #define LGCN_E_BAD_DIM   (-1) /* embedding dim not supported              */
 #define LGCN_E_BAD_ARG   (-2) /* null pointer / negative size / bad mode  */
@@ -80,11 +80,20 @@ LGCN_API int lgcn_edge_weights(const int32_t *rowptr, const int32_t *col, const 
  *    entries live in `long_colval` (CSR over the long rows, `long_rowptr`), are cut into
  *    segments of seg_len entries, one sub-warp per segment, partial sums staged in seg_ws and
  *    combined in segment order (deterministic, not bit-equal to the sequential order).
+ *  - L2 residency classes (optional, set by the graph plan when the tables exceed L2; honoured
+ *    under LGCN_SPMM_F_STREAM_HINTS, always masked off): bit 31 of colval[e].col marks a HOT
+ *    column -- one of the highest-degree nodes, as many as the L2 budget holds -- whose gathered
+ *    row is kept with evict_last; bit 30 marks a column referenced exactly once per launch
+ *    (degree 1), whose row leaves L2 first.  Column ids therefore need n_cols <= 2^30.
+ *    `long_colval` carries no class bits.
  * ------------------------------------------------------------------------------------- */
 typedef struct lgcn_colval {
     int32_t col;
     float   val;
 } lgcn_colval;
+#define LGCN_COL_HOT  ((int32_t)0x80000000)
+#define LGCN_COL_ONCE 0x40000000
+#define LGCN_COL_MASK 0x3fffffff
 
 typedef struct lgcn_spmm_args {
     const uint32_t    *rowptr;  /* [n_rows+1] entry offsets, bit 31 = long-row flag       */
@@ -122,6 +131,11 @@ typedef struct lgcn_spmm_args {
     const uint8_t *x_rowflag;
     const uint8_t *addend_rowflag;
     const float   *zero_row;
+    /* Sparse OUTPUT (mode ADD with x_rowflag and addend_rowflag only, optional): the kernel sets
+     * y_rowflag[r] = 1 for the rows that summed a flagged row of x or have a flagged addend
+     * (and for long rows), 0 for the others, and does NOT write the all-zero rows of y -- the
+     * consumer must read y under y_rowflag (it is the next hop's x_rowflag).  [n_rows]. */
+    uint8_t       *y_rowflag;
 } lgcn_spmm_args;
 
 /* tables do not fit L2: stream entries / outputs / epilogue operands with L2 evict_first so
@@ -130,6 +144,7 @@ typedef struct lgcn_spmm_args {
 /* kernel selection overrides for tests and A/B measurements (default: chosen by d and mode) */
 #define LGCN_SPMM_F_NO_RING 2       /* register-batch chunk kernel only                      */
 #define LGCN_SPMM_F_BIG_PATH 4      /* large-graph kernels even when the graph is small      */
+#define LGCN_SPMM_F_COLD_FIRST 8    /* gathers of unclassified columns use evict_first too   */
 #define LGCN_SPMM_F_FORCE_RING 16   /* cp.async ring kernel for the ADAM epilogue too        */
 
 #define LGCN_SPMM_PLAIN 0 /* y = A x                                                    */

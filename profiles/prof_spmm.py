@@ -16,7 +16,7 @@ workload = sys.argv[1] if len(sys.argv) > 1 else "amazon"
 mode = sys.argv[2] if len(sys.argv) > 2 else "plain"
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 dev = torch.device("cuda:0")
-ops.SPMM_FLAGS_EXTRA = int(os.environ.get("LGCN_SPMM_FLAGS", "0"))   # 2 = chunk kernel instead of ring
+# LGCN_SPMM_FLAGS (read by ops): 2 = chunk kernel instead of ring, 16 = ring for the ADAM epilogue too
 U, I, B, total, d, K = synth.SHAPES[workload]
 if len(sys.argv) > 4:
     d = int(sys.argv[4])
@@ -35,12 +35,13 @@ if mode == "addflag":     # a later Horner hop: dense x, addend g' with 3*2048 n
     flag = torch.zeros(N + 32, dtype=torch.uint8, device=dev)
     flag[rows] = 1
     zero_row = torch.zeros(256, device=dev)
-if mode == "hop1":        # the first Horner hop: x = g' has 3*2048 non-zero rows, flagged
+if mode in ("hop1", "hop1s"):        # the first Horner hop: x = g' has 3*2048 non-zero rows, flagged
     rows = torch.randint(0, N, (6144,), device=dev)
     x.zero_()
     x[rows] = torch.randn((6144, d), device=dev)
-    flag = torch.zeros(N, dtype=torch.uint8, device=dev)
+    flag = torch.zeros(N + 32, dtype=torch.uint8, device=dev)
     flag[rows] = 1
+    yflag = torch.zeros(N + 32, dtype=torch.uint8, device=dev)
     zero_row = torch.zeros(256, device=dev)
     add = x
 torch.cuda.synchronize()
@@ -55,6 +56,9 @@ for i in range(n):
         ops.spmm(g, x, out=y, addend=add, addend_rowflag=flag, zero_row=zero_row)
     elif mode == "hop1":
         ops.spmm(g, x, out=y, addend=add, x_rowflag=flag, addend_rowflag=flag, zero_row=zero_row)
+    elif mode == "hop1s":     # + sparse output (all-zero rows not written, reported in yflag)
+        ops.spmm(g, x, out=y, addend=add, x_rowflag=flag, addend_rowflag=flag, zero_row=zero_row,
+                 y_rowflag=yflag)
     elif mode == "mean":
         ops.spmm(g, x, out=y, mean_layers=[add, x, add, x][:K])
     ev[i + 1].record()

@@ -100,11 +100,13 @@ def test_spmm_bit_exact_all_dims(dev, d):
 
 
 @pytest.mark.parametrize("d", [16, 32, 64, 128, 256])
-@pytest.mark.parametrize("kernel", ["ring", "chunk"])
+@pytest.mark.parametrize("kernel", ["ring", "chunk", "ring_hot", "chunk_hot"])
 def test_spmm_large_graph_kernels_bit_exact(dev, d, kernel):
     """The large-graph kernels (cp.async ring kernel / 16-row register-batch chunks) forced onto
     a small graph: every epilogue bit-exact against the oracle, with short-row/long-row mixes,
-    empty rows and a ragged last worker."""
+    empty rows and a ragged last worker.  The ``_hot`` variants also force the streaming L2 hints
+    and the column residency classes (300 hot columns, degree-1 columns evict_first): the class
+    bits of the packed column index must never reach the address arithmetic."""
     from gcn_recommendation_b200 import _lib, ops, synth
     from gcn_recommendation_b200.graph import NormAdjCSR
     orc = _orc()
@@ -118,14 +120,23 @@ def test_spmm_large_graph_kernels_bit_exact(dev, d, kernel):
     A1 = rng.standard_normal((N, d), dtype=np.float32)
     A2 = rng.standard_normal((N, d), dtype=np.float32)
     ref = orc.spmm(a["rowptr"], a["col"], a["val"], X)
-    old = ops.SPMM_FLAGS_EXTRA
-    ops.SPMM_FLAGS_EXTRA = _lib.SPMM_F_BIG_PATH | (_lib.SPMM_F_NO_RING if kernel == "chunk"
+    old, old_hot = ops.SPMM_FLAGS_EXTRA, ops.HOT_BYTES
+    ops.SPMM_FLAGS_EXTRA = _lib.SPMM_F_BIG_PATH | (_lib.SPMM_F_NO_RING if kernel.startswith("chunk")
                                                       else _lib.SPMM_F_FORCE_RING)
+    hot = kernel.endswith("_hot")
+    if hot:
+        ops.SPMM_FLAGS_EXTRA |= _lib.SPMM_F_STREAM_HINTS | (_lib.SPMM_F_COLD_FIRST if d == 64 else 0)
+        ops.HOT_BYTES = 300 * 4 * d
     try:
         for thr in (0, 64):          # 0: every row on the sequential path; 64: hot items segmented
             csr = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev, long_row_threshold=thr, seg_len=32)
             short = np.diff(a["rowptr"]) <= (thr if thr else 1 << 30)
             xt = _t(X, dev)
+            if hot:
+                ops.spmm(csr, xt)
+                c0 = csr.colval[:, 0]
+                assert int((c0 < 0).sum()) > 0 and int(((c0 >> 30) & 1).sum()) > 0
+                assert csr.n_hot == 300
             Y = ops.spmm(csr, xt).cpu().numpy()
             assert np.array_equal(_bits(Y[short]), _bits(ref[short]))
             assert rel_err(Y, ref)[0] < TOL
@@ -153,6 +164,37 @@ def test_spmm_large_graph_kernels_bit_exact(dev, d, kernel):
             want = A1 + orc.spmm(a["rowptr"], a["col"], a["val"], Xs)
             assert np.array_equal(_bits(Yx[short]), _bits(want[short]))
             assert rel_err(Yx, want)[0] < TOL
+            # sparse OUTPUT: addend g' flagged like x (the first Horner hop); all-zero output rows
+            # are reported in y_rowflag and left unwritten (the buffer is NaN-poisoned), and the
+            # next hop gathers under those flags (zero rows of its input still poisoned)
+            nz2 = rng.choice(N, 40, replace=False)
+            G = np.zeros((N, d), np.float32)
+            G[nz2] = rng.standard_normal((40, d), dtype=np.float32)
+            gflag = np.zeros(N + 32, np.uint8)
+            gflag[nz2] = 1
+            Xp = G.copy()
+            Xp[gflag[:N] == 0] = np.nan
+            ft = _t(gflag, dev, torch.uint8)
+            yflag = torch.full((N + 32,), 7, dtype=torch.uint8, device=dev)
+            out1 = torch.full((N, d), float("nan"), device=dev)
+            ops.spmm(csr, _t(Xp, dev), out=out1, addend=_t(G, dev), x_rowflag=ft, addend_rowflag=ft,
+                     zero_row=zr, y_rowflag=yflag)
+            hop1 = G + orc.spmm(a["rowptr"], a["col"], a["val"], G)
+            yf = yflag[:N].cpu().numpy()
+            assert set(np.unique(yf)) <= {0, 1}
+            nz = np.abs(hop1).max(axis=1) > 0
+            assert not (nz & (yf == 0)).any(), "a non-zero row was reported as zero"
+            assert 40 <= yf.sum() < 0.5 * N
+            o1 = out1.cpu().numpy()
+            assert np.isnan(o1[yf == 0]).all(), "an all-zero row was written"
+            live = (yf == 1) & short
+            assert np.array_equal(_bits(o1[live]), _bits(hop1[live]))
+            assert rel_err(o1[yf == 1], hop1[yf == 1])[0] < TOL
+            out2 = ops.spmm(csr, out1, addend=_t(G, dev), x_rowflag=yflag, addend_rowflag=ft,
+                            zero_row=zr).cpu().numpy()
+            hop2 = G + orc.spmm(a["rowptr"], a["col"], a["val"], hop1)
+            assert np.array_equal(_bits(out2[short]), _bits(hop2[short])) or thr
+            assert rel_err(out2, hop2)[0] < TOL
         # Adam epilogue against the standalone Adam kernel fed with the same gradient
         csr = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev, long_row_threshold=0)
         xt = _t(X, dev)
@@ -169,7 +211,7 @@ def test_spmm_large_graph_kernels_bit_exact(dev, d, kernel):
         for x1, x2 in ((p1, p2), (m1, m2), (v1, v2)):
             assert torch.equal(x1, x2)
     finally:
-        ops.SPMM_FLAGS_EXTRA = old
+        ops.SPMM_FLAGS_EXTRA, ops.HOT_BYTES = old, old_hot
 
 
 @pytest.mark.parametrize("d", [64, 128])

@@ -118,6 +118,35 @@ def test_long_row_plan_host_logic():
     assert torch.equal(g0.rowptr_flagged, g0.rowptr)
 
 
+def test_column_residency_classes_host_logic():
+    """include/lgcn.h LGCN_COL_*: the n_hot highest-degree nodes carry bit 31 in the packed column
+    index, degree-1 nodes bit 30, the low 30 bits stay the column id; clearing restores it."""
+    from gcn_recommendation_b200 import synth
+    from oracle import lgcn_oracle as orc
+    from gcn_recommendation_b200.graph import NormAdjCSR
+    inter = synth.generate("tiny", seed=3)
+    tu, ti, _, _ = inter.split_validation()
+    U, I, B = inter.num_users, inter.num_items, inter.num_brands
+    a = orc.build_norm_adj(tu, ti, U, I, B)
+    g = NormAdjCSR(torch.from_numpy(a["rowptr"].astype(np.int32)), torch.from_numpy(a["col"].astype(np.int32)),
+                   torch.from_numpy(a["val"]), U + I + B, long_row_threshold=0)
+    plain = g.colval[:, 0].clone()
+    g.mark_hot_columns(25)
+    raw = g.colval[:, 0]
+    assert torch.equal(raw & 0x3fffffff, plain)
+    deg = np.diff(a["rowptr"])
+    cols = plain.numpy()
+    hot = (raw < 0).numpy()
+    once = (((raw >> 30) & 1) == 1).numpy() & ~hot
+    assert np.array_equal(once, deg[cols] == 1)
+    kth = np.sort(deg)[-25]
+    assert hot[deg[cols] > kth].all() and not hot[deg[cols] < kth].any()
+    assert len(np.unique(cols[hot])) <= 25 and hot.any()
+    g.mark_hot_columns(0)
+    assert torch.equal(g.colval[:, 0], plain)
+    assert torch.equal(g.colval[:, 1], torch.from_numpy(a["val"]).view(torch.int32))
+
+
 def test_mask_csr_matches_groupby_lists():
     from gcn_recommendation_b200.engine import build_mask_csr
     tu = np.array([3, 1, 3, 0, 1, 3], np.int64)
