@@ -20,9 +20,11 @@ from ._lib import SPMM_ADAM, SPMM_ADD, SPMM_MEAN, SPMM_PLAIN, SpmmArgs, check, p
 COUNTERS = {"launches": 0}
 L2_STREAM_BYTES = 96 << 20      # tables larger than this are streamed with L2 evict_first hints
 PROFILE = None
-# L2 budget for the gathered rows of the highest-degree columns (kept with evict_last; the rows of
-# degree-1 columns leave first): LGCN_HOT_MB=0 turns the column classes off.
-HOT_BYTES = int(float(os.environ.get("LGCN_HOT_MB", "64")) * (1 << 20))
+# L2 budget for the gathered rows of the highest-degree columns (gathered with evict_last; the rows
+# of degree-1 columns leave first): LGCN_HOT_MB=0 turns the column classes off.  Measured at the
+# Amazon shape (profiles/r01_hot_columns_sweep.txt): 32 MB is best, and worth only 0.5-2 % -- the
+# L2 does not retain the hot rows under 6 TB/s of streaming (sector hit rate 11.5 -> 12.9 %).
+HOT_BYTES = int(float(os.environ.get("LGCN_HOT_MB", "32")) * (1 << 20))
 SPMM_FLAGS_EXTRA = int(os.environ.get("LGCN_SPMM_FLAGS", "0"))           # OR-ed into lgcn_spmm_args.flags (tests / A-B measurements force a kernel)
 
 

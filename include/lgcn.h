@@ -83,7 +83,8 @@ LGCN_API int lgcn_edge_weights(const int32_t *rowptr, const int32_t *col, const 
  *  - L2 residency classes (optional, set by the graph plan when the tables exceed L2; honoured
  *    under LGCN_SPMM_F_STREAM_HINTS, always masked off): bit 31 of colval[e].col marks a HOT
  *    column -- one of the highest-degree nodes, as many as the L2 budget holds -- whose gathered
- *    row is kept with evict_last; bit 30 marks a column referenced exactly once per launch
+ *    row is gathered with evict_last (a preference only: measured +0.5..2 % at the Amazon shape;
+ *    an L2 persisting set-aside on top of it made the streams slower); bit 30 marks a column referenced exactly once per launch
  *    (degree 1), whose row leaves L2 first.  Column ids therefore need n_cols <= 2^30.
  *    `long_colval` carries no class bits.
  * ------------------------------------------------------------------------------------- */

@@ -364,6 +364,35 @@ def test_engine_training_matches_reference(golden, dev, case, use_graph):
     assert not eng.G1.any() and not eng.G2.any()
 
 
+@pytest.mark.parametrize("fusion", [False, True])
+def test_engine_sparse_backward_hops_are_bit_identical(golden, dev, fusion):
+    """The sparse-gradient shortcuts (first Horner hop writes only its non-zero rows, second hop
+    gathers under those flags) skip exact zeros only: parameters and Adam moments after several
+    steps are bit-identical to the dense hops (LightGCN; the fusion variant within 1e-6)."""
+    case = "tiny_fusion_d64_k3" if fusion else "tiny_lightgcn_d128_k4"
+    g = golden(case)
+    csr = _graph(g, dev)
+    out = []
+    for sparse in (False, True):
+        model = _model(g, case, dev)
+        eng = model.engine(csr, lr=float(g["lr"]), weight_decay=float(g["lam"]), batch_size=int(g["bs"]))
+        eng.sparse_hops = sparse
+        for s in range(4):
+            # distinct rows per batch: the scatter's atomics then have one addend per element, so
+            # the two runs can be compared bit for bit
+            u = (torch.arange(48, device=dev) + 7 * s) % int(g["num_users"])
+            p = (torch.arange(48, device=dev) + 11 * s) % 90
+            n = 100 + (torch.arange(48, device=dev) + 13 * s) % 90
+            eng.bpr_step(u, p, n, use_graph=False)
+        assert bool(eng.rowflag2.any()) == sparse
+        out.append((eng.P.clone(), eng.m.clone(), eng.v.clone(), eng.loss.clone()))
+    for a, b in zip(*out):
+        if fusion:      # dW/db are reduced with atomics: run-to-run rounding noise, not bit-stable
+            assert rel_err(a.cpu().numpy(), b.cpu().numpy())[1] < 1e-6
+        else:
+            assert torch.equal(a, b)
+
+
 def test_bpr_fused_vs_oracle_with_duplicates(dev):
     from gcn_recommendation_b200 import ops
     orc = _orc()

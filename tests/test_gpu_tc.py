@@ -112,7 +112,20 @@ def test_amazon_shape_properties(dev):
     dense = ops.spmm(csr, xs, addend=xs)
     sparse = ops.spmm(csr, xs, addend=xs, x_rowflag=flag, zero_row=zero_row)
     assert torch.equal(dense, sparse)
-    del dense, sparse, xs, y
+    # ... and the sparse-OUTPUT chain of the backward pass (live-list kernel): hop 1 writes only
+    # the rows it can make non-zero and reports them, hop 2 gathers under those flags; the
+    # result equals two dense hops bit for bit, the unwritten rows are never read (NaN-poisoned)
+    yflag = torch.zeros(N + 32, dtype=torch.uint8, device=dev)
+    h1 = torch.full_like(x, float("nan"))
+    ops.spmm(csr, xs, out=h1, addend=xs, x_rowflag=flag, addend_rowflag=flag, zero_row=zero_row,
+             y_rowflag=yflag)
+    live = yflag[:N].bool()
+    assert 6000 < int(live.sum()) < N // 2
+    assert torch.equal(h1[live], dense[live]) and not bool(dense[~live].any())
+    assert bool(torch.isnan(h1[~live]).all())
+    h2 = ops.spmm(csr, h1, addend=xs, x_rowflag=yflag, addend_rowflag=flag, zero_row=zero_row)
+    assert torch.equal(h2, ops.spmm(csr, dense, addend=xs))
+    del dense, sparse, xs, y, h1, h2
     # rating over the full 4.4 M-item catalogue
     Fu, Fi = ax[:U], ax[U:U + I]
     eu = vu[:256].contiguous()
