@@ -116,8 +116,15 @@ __device__ __forceinline__ void adam_elem(float &p, float &m, float &v, float g,
                                           float bc2_sqrt, float beta1, float beta2, float eps) {
     m = __fmaf_rn(__fsub_rn(g, m), 1.0f - beta1, m);
     v = __fmaf_rn((1.0f - beta2) * g, g, v * beta2);
+#ifdef LGCN_ADAM_FAST     // A/B only: approximate sqrt / divisions (2 ulp each)
+    float sq;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(v));
+    const float denom = __fadd_rn(__fdividef(sq, bc2_sqrt), eps);
+    p = __fsub_rn(p, step_size * __fdividef(m, denom));
+#else
     const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), eps);
     p = __fsub_rn(p, step_size * __fdiv_rn(m, denom));
+#endif
 }
 
 __device__ __forceinline__ void adam4(float4 &p, float4 &m, float4 &v, const float4 &g, float ss,

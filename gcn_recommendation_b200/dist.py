@@ -143,12 +143,34 @@ class FeatureShardedEngine(LightGCNEngine):
                       gp_includes_gf=gp_includes_gf, sample_ws=self.sample_ws, loss_out=self.loss,
                       rowflag=self.rowflag)
 
+    # ---- reference-format checkpoints from column shards -------------------------
+    def _gather_columns(self, local):
+        rows, dl = local.shape
+        out = torch.empty((self.world * rows, dl), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+        return out.view(self.world, rows, dl).permute(1, 0, 2).reshape(rows, self.world * dl).contiguous()
+
+    def _full_table(self):
+        return self._gather_columns(self.P)
+
+    def _local_columns(self, full):
+        dl = self.d
+        if full.shape[1] != dl * self.world:
+            raise LgcnError(f"checkpoint width {full.shape[1]} != {dl * self.world}")
+        return full[:, self.rank * dl:(self.rank + 1) * dl]
+
+    def _full_content(self):
+        C = self.fusion["C"]                                        # this rank's item block
+        pad = torch.zeros((self.ipr, C.shape[1]), dtype=C.dtype, device=C.device)
+        pad[:C.shape[0]].copy_(C)
+        out = torch.empty((self.world * self.ipr, C.shape[1]), dtype=C.dtype, device=C.device)
+        dist.all_gather_into_tensor(out, pad, group=self.group)
+        return out[:self.I]
+
     def gather_final_table(self):
         """All-gather the propagated table over the feature dimension -> [N, d] on every rank."""
         F = self.propagate()
-        out = torch.empty((self.world,) + tuple(F.shape), dtype=F.dtype, device=F.device)
-        dist.all_gather_into_tensor(out, F.contiguous(), group=self.group)
-        return out.permute(1, 0, 2).reshape(F.shape[0], self.world * F.shape[1]).contiguous()
+        return self._gather_columns(F)
 
     def evaluate(self, eval_users, targets, mask_rowptr, mask_col, k=20, propagate=True):
         """User-sharded full-rank evaluation (reference ``main.py:404-439``): the caller passes

@@ -284,6 +284,53 @@ class LightGCNEngine:
                 self._step_body()
         return self.loss
 
+    # ---- checkpoints in the reference's format (main.py:550 saves model.state_dict()) ---------
+    def _full_table(self):
+        return self.P
+
+    def _local_columns(self, full):
+        return full
+
+    def _full_content(self):
+        return self.fusion["C"]
+
+    def state_dict(self):
+        """The parameters under the reference's ``state_dict`` keys (``models/lightgcn.py:15-17``,
+        ``models/lightgcn_fusion.py:20-35``; same key order), as CPU tensors -- what
+        ``torch.save(model.state_dict(), ...)`` of reference ``main.py:550`` would hold, whatever
+        the sharding.  Collective when the engine is sharded (every rank gets the full dict)."""
+        from collections import OrderedDict
+        U, I = self.U, self.I
+        P = self._full_table().detach().cpu()
+        sd = OrderedDict()
+        if self.fusion is None:
+            sd["user_embedding.weight"] = P[:U].clone()
+            sd["brand_embedding.weight"] = P[U + I:].clone()
+            sd["item_embedding.weight"] = P[U:U + I].clone()
+        else:
+            sd["item_content_embedding"] = self._full_content().detach().cpu().clone()
+            sd["user_embedding.weight"] = P[:U].clone()
+            sd["item_id_embedding.weight"] = P[U:U + I].clone()
+            sd["brand_embedding.weight"] = P[U + I:].clone()
+            sd["item_fusion_layer.weight"] = self.fusion["W"].detach().cpu().clone()
+            sd["item_fusion_layer.bias"] = self.fusion["b"].detach().cpu().clone()
+        return sd
+
+    def load_state_dict(self, sd):
+        """Load a reference-format checkpoint (``main.py:571``) into the (possibly sharded)
+        tables.  Optimizer state is not part of the reference's checkpoints and is left as is."""
+        U, I, B = self.U, self.I, self.B
+        item_key = "item_embedding.weight" if self.fusion is None else "item_id_embedding.weight"
+        parts = [sd["user_embedding.weight"], sd[item_key], sd["brand_embedding.weight"]]
+        for t, rows in zip(parts, (U, I, B)):
+            if tuple(t.shape[:1]) != (rows,):
+                raise LgcnError(f"checkpoint table has {t.shape[0]} rows, expected {rows}")
+        full = torch.cat([t.to(torch.float32) for t in parts], 0)
+        self.P.copy_(self._local_columns(full))
+        if self.fusion is not None:
+            self.fusion["W"].copy_(sd["item_fusion_layer.weight"])
+            self.fusion["b"].copy_(sd["item_fusion_layer.bias"])
+
     def bpr_loss(self, users, pos, neg):
         """Loss only (no gradient, no update) on the current parameters."""
         F = self.propagate()

@@ -70,6 +70,37 @@ def _worker(rank, world, port, q):
         assert torch.equal(rows[:i1 - i0], Ei[i0:i1])
         back = rows_to_cols(rows, a_in, a_out, torch.zeros((I, dl)), a2a)
         assert torch.equal(back, Ei[:, rank * dl:(rank + 1) * dl])
+        # ---- reference-format checkpoints from feature-sharded engines (round trip) ----------
+        from gcn_recommendation_b200.dist import FeatureShardedEngine, column_shard
+        from gcn_recommendation_b200.graph import NormAdjCSR
+        csr = NormAdjCSR(torch.from_numpy(a["rowptr"].astype(np.int32)),
+                         torch.from_numpy(a["col"].astype(np.int32)), torch.from_numpy(a["val"]), N)
+        table = torch.from_numpy(E0)
+        eng = FeatureShardedEngine(csr, U, I, B, K, column_shard(table, rank, world), batch_size=8)
+        sd = eng.state_dict()
+        assert list(sd.keys()) == ["user_embedding.weight", "brand_embedding.weight", "item_embedding.weight"]
+        for k in sd:
+            assert torch.equal(sd[k], torch.from_numpy(g["init/" + k])), k
+        eng2 = FeatureShardedEngine(csr, U, I, B, K, torch.zeros((N, dl)), batch_size=8)
+        eng2.load_state_dict(sd)
+        assert torch.equal(eng2.P, eng.P)
+        # fusion variant: content sharded by item block, W / b replicated
+        gen = torch.Generator().manual_seed(5)
+        c = 12
+        Cfull = torch.randn((I, c), generator=gen)
+        W = torch.randn((d, d + c), generator=gen)
+        bb = torch.randn((d,), generator=gen)
+        fus = dict(content=Cfull[i0:i1].contiguous(), weight=W.clone(), bias=bb.clone(),
+                   alltoall=a2a, allreduce=lambda t: dist.all_reduce(t))
+        engf = FeatureShardedEngine(csr, U, I, B, K, column_shard(table, rank, world), batch_size=8,
+                                    fusion=fus)
+        sdf = engf.state_dict()
+        assert list(sdf.keys()) == ["item_content_embedding", "user_embedding.weight",
+                                    "item_id_embedding.weight", "brand_embedding.weight",
+                                    "item_fusion_layer.weight", "item_fusion_layer.bias"]
+        assert torch.equal(sdf["item_content_embedding"], Cfull)
+        assert torch.equal(sdf["item_id_embedding.weight"], table[U:U + I])
+        assert torch.equal(sdf["item_fusion_layer.weight"], W)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))

@@ -147,6 +147,34 @@ def test_column_residency_classes_host_logic():
     assert torch.equal(g.colval[:, 1], torch.from_numpy(a["val"]).view(torch.int32))
 
 
+def test_engine_checkpoint_is_reference_format():
+    """``engine.state_dict()`` has the reference's keys / order / shapes and loads into the
+    reference-compatible drop-in module (reference ``main.py:550,571``)."""
+    import types
+    from gcn_recommendation_b200.engine import LightGCNEngine
+    from gcn_recommendation_b200.graph import NormAdjCSR
+    from models.lightgcn import LightGCN
+    U, I, B, d = 5, 7, 1, 64
+    N = U + I + B
+    rowptr = torch.zeros(N + 1, dtype=torch.int32)
+    g = NormAdjCSR(rowptr, torch.zeros(0, dtype=torch.int32), torch.zeros(0), N)
+    table = torch.randn((N, d))
+    eng = LightGCNEngine(g, U, I, B, 3, table.clone())
+    sd = eng.state_dict()
+    m = LightGCN(U, I, B, types.SimpleNamespace(embedding_dim=d, n_layers=3, debug=False))
+    assert list(sd.keys()) == list(m.state_dict().keys())
+    m.load_state_dict(sd)                                   # strict: every key and shape matches
+    assert torch.equal(m.item_embedding.weight, table[U:U + I])
+    eng2 = LightGCNEngine(g, U, I, B, 3, torch.zeros((N, d)))
+    eng2.load_state_dict(m.state_dict())
+    assert torch.equal(eng2.P, table)
+    from gcn_recommendation_b200._lib import LgcnError
+    bad = dict(sd)
+    bad["user_embedding.weight"] = torch.zeros((U + 1, d))
+    with pytest.raises(LgcnError):
+        eng2.load_state_dict(bad)
+
+
 def test_mask_csr_matches_groupby_lists():
     from gcn_recommendation_b200.engine import build_mask_csr
     tu = np.array([3, 1, 3, 0, 1, 3], np.int64)
