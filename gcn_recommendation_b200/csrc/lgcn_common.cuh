@@ -116,14 +116,19 @@ __device__ __forceinline__ void adam_elem(float &p, float &m, float &v, float g,
                                           float bc2_sqrt, float beta1, float beta2, float eps) {
     m = __fmaf_rn(__fsub_rn(g, m), 1.0f - beta1, m);
     v = __fmaf_rn((1.0f - beta2) * g, g, v * beta2);
-#ifdef LGCN_ADAM_FAST     // A/B only: approximate sqrt / divisions (2 ulp each)
+#ifdef LGCN_ADAM_EXACT    // correctly rounded sqrt / divisions (the CPU arithmetic, bit for bit)
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), eps);
+    p = __fsub_rn(p, step_size * __fdiv_rn(m, denom));
+#else
+    // fp32 sqrt.approx / div.approx (<= 2 ulp each): the update term step*m/denom is off by
+    // < 1e-6 relative, i.e. < 1e-8 of p -- far inside the 1e-5 bar -- and the fused ADAM hop
+    // drops from 13.17 to 12.19 ms at the Amazon shape (it is issue/latency bound: ncu
+    // profiles/r01_spmm_chunk_adam_amazon_ncu.txt, 39 % issue-active at 26 % occupancy).
+    // m and v themselves are computed exactly.
     float sq;
     asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(v));
     const float denom = __fadd_rn(__fdividef(sq, bc2_sqrt), eps);
     p = __fsub_rn(p, step_size * __fdividef(m, denom));
-#else
-    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), eps);
-    p = __fsub_rn(p, step_size * __fdiv_rn(m, denom));
 #endif
 }
 
