@@ -245,12 +245,25 @@ __device__ __forceinline__ unsigned sparse_out_mask(const lgcn_spmm_args &a, con
     return wmask;
 }
 
+template <int D>
+__device__ __forceinline__ void long_seg_body(const lgcn_spmm_args &a, int64_t block);
+
 // ---- main kernel: one worker per chunk of R rows ---------------------------------------------
 template <int D, int MODE, int RSEL, bool HINT, bool XF>
 __global__ void __launch_bounds__(kThreads, (MODE == LGCN_SPMM_PLAIN || MODE == LGCN_SPMM_ADD) ? LGCN_SPMM_MINBLOCKS_LIGHT : LGCN_SPMM_MINBLOCKS)
 spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
     using G = RowGeom<D>;
     using C = ChunkCfg<D, RSEL>;
+    if constexpr (RSEL == 1) {
+        // small (L2-resident, latency-bound) graphs: the long-row segment workers ride in the same
+        // launch as extra CTAs, so the two independent phases overlap (Gowalla shape: the separate
+        // 31 us segment launch was a quarter of an SpMM call)
+        const int64_t cb = (a.n_rows + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
+        if ((int64_t)blockIdx.x >= cb) {
+            long_seg_body<D>(a, (int64_t)blockIdx.x - cb);
+            return;
+        }
+    }
     const uint64_t pol = HINT ? policy_evict_first() : 0ull;
     const GatherPolicy gpol = gather_policy<HINT && !XF>(a.flags, pol);
     extern __shared__ __align__(16) float stage_all[];
@@ -742,12 +755,12 @@ spmm_live_kernel(const __grid_constant__ lgcn_spmm_args a) {
 
 // ---- long rows: one worker per segment, partial sums to seg_ws -----------------------------
 template <int D>
-__global__ void __launch_bounds__(kThreads) spmm_long_seg_kernel(const __grid_constant__ lgcn_spmm_args a) {
+__device__ __forceinline__ void long_seg_body(const lgcn_spmm_args &a, int64_t block) {
     using G = RowGeom<D>;
     const int lane = threadIdx.x & 31;
     const int grp = lane / G::LANES;
     const int sub = lane % G::LANES;
-    const int64_t warp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const int64_t warp = block * kWarps + (threadIdx.x >> 5);
     const int64_t seg = warp * G::GROUPS + grp;
     int beg = 0, deg = 0;
     if (seg < a.n_seg) {
@@ -809,6 +822,11 @@ __global__ void __launch_bounds__(kThreads) spmm_long_seg_kernel(const __grid_co
     }
 }
 
+template <int D>
+__global__ void __launch_bounds__(kThreads) spmm_long_seg_kernel(const __grid_constant__ lgcn_spmm_args a) {
+    long_seg_body<D>(a, (int64_t)blockIdx.x);
+}
+
 // ---- long rows: combine the segment partials in order, then the epilogue -------------------
 template <int D, int MODE>
 __global__ void __launch_bounds__(kThreads) spmm_long_combine_kernel(const __grid_constant__ lgcn_spmm_args a) {
@@ -856,7 +874,9 @@ static int launch_chunks(const lgcn_spmm_args &a, cudaStream_t st) {
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
-    const int64_t gb = (a.n_rows + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
+    int64_t gb = (a.n_rows + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
+    if (RSEL == 1 && a.n_long > 0)          // + the long-row segment workers (see the kernel)
+        gb += (a.n_seg + kWarps * RowGeom<D>::GROUPS - 1) / (kWarps * RowGeom<D>::GROUPS);
     if (gb > 0x7fffffffLL) return LGCN_E_TOO_LARGE;
     spmm_chunk_kernel<D, MODE, RSEL, HINT, XF><<<(unsigned)gb, kThreads, C::SMEM, st>>>(a);
     LGCN_LAUNCH_CHECK();
@@ -901,15 +921,15 @@ template <int D, int MODE>
 static int launch_mode(const lgcn_spmm_args &a, cudaStream_t st) {
     using G = RowGeom<D>;
     constexpr int groups_per_block = kWarps * G::GROUPS;
-    if (a.n_long > 0) {
+    // small graphs: 4-row chunks so that the chip is filled (>= ~2 waves of workers)
+    const int64_t big_workers = a.n_rows / ChunkCfg<D, 0>::R;
+    const bool small = big_workers < (int64_t)kNumSMs * 32 * G::GROUPS && !(a.flags & LGCN_SPMM_F_BIG_PATH);
+    if (a.n_long > 0 && !(small && a.n_rows > 0)) {     // small graphs: inside the chunk launch
         const unsigned gs = (unsigned)((a.n_seg + groups_per_block - 1) / groups_per_block);
         spmm_long_seg_kernel<D><<<gs, kThreads, 0, st>>>(a);
         LGCN_LAUNCH_CHECK();
     }
     if (a.n_rows > 0) {
-        // small graphs: 4-row chunks so that the chip is filled (>= ~2 waves of workers)
-        const int64_t big_workers = a.n_rows / ChunkCfg<D, 0>::R;
-        const bool small = big_workers < (int64_t)kNumSMs * 32 * G::GROUPS && !(a.flags & LGCN_SPMM_F_BIG_PATH);
         const bool hint = (a.flags & LGCN_SPMM_F_STREAM_HINTS) != 0;
         int rc;
         const bool xf = MODE == LGCN_SPMM_ADD && a.x_rowflag != nullptr;

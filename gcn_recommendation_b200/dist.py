@@ -233,7 +233,7 @@ class RowShardedEngine:
         self.sample_ws = torch.empty(2 * self.bs, dtype=torch.float32, device=self.dev)
         self.Gfull = torch.zeros((self.rpr * P_, self.d), dtype=torch.float32, device=self.dev)
         self.G2full = torch.zeros((self.rpr * P_, self.d), dtype=torch.float32, device=self.dev)
-        per_spmm = 3 if (self.g is not None and self.g.n_long > 0) else 1
+        per_spmm = ops.spmm_launches(self.g, self.d) if self.g is not None else 1
         self.launches_per_step = 2 * self.K * per_spmm + 2 + 1 + 1
         self.collectives_per_step = 2 * self.K
 

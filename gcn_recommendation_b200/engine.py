@@ -133,7 +133,7 @@ class LightGCNEngine:
 
     def _count_launches(self):
         """Kernels of THIS library launched per training step (for bench.py's gpu_launches)."""
-        per_spmm = 3 if self.g.n_long > 0 else 1
+        per_spmm = ops.spmm_launches(self.g, self.d)
         n = 2 * self.K * per_spmm + 2 + 1 + 1          # spmm fwd+bwd, bpr(+reduce), tick, zero
         if self.fusion is not None:
             n += 1 + 2 + 5                             # proj fwd, proj bwd (2), 5 adam launches

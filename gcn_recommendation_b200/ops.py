@@ -28,8 +28,24 @@ HOT_BYTES = int(float(os.environ.get("LGCN_HOT_MB", "32")) * (1 << 20))
 SPMM_FLAGS_EXTRA = int(os.environ.get("LGCN_SPMM_FLAGS", "0"))           # OR-ed into lgcn_spmm_args.flags (tests / A-B measurements force a kernel)
 
 
+def _small_graph(n_rows, d):
+    """Mirror of the kernel selection in csrc/lgcn_spmm.cu ``launch_mode``: graphs with too few
+    16-row chunks to fill the chip run 4-row chunks (and carry the long-row segment workers in
+    the same launch)."""
+    lanes = min(32, d // 4)
+    rbig = min(lanes, max(4, 2048 // d))
+    return (n_rows // rbig) < 148 * 32 * (32 // lanes) and not (SPMM_FLAGS_EXTRA & _lib.SPMM_F_BIG_PATH)
+
+
+def spmm_launches(g, d):
+    """Kernels one ``lgcn_spmm`` call launches for this graph / width."""
+    if g.n_long == 0:
+        return 1
+    return 2 if _small_graph(g.n_rows, d) else 3
+
+
 def _launch_spmm(a, g, dev, tag):
-    n_kernels = 3 if a.n_long > 0 else 1
+    n_kernels = spmm_launches(g, a.d)
     COUNTERS["launches"] += n_kernels
     if PROFILE is None:
         check(_lib.load().lgcn_spmm(ctypes.byref(a), stream_ptr(dev)))
@@ -67,10 +83,7 @@ def _spmm_args(g, x, mode, d):
 def spmm_kernel_name(g, d, mode):
     """Name of the kernel ``lgcn_spmm`` picks for this graph / width / mode (mirrors the selection
     in csrc/lgcn_spmm.cu ``launch_mode``; used by bench.py to label the roofline)."""
-    lanes = min(32, d // 4)
-    groups = 32 // lanes
-    rbig = min(lanes, max(4, 2048 // d))
-    if (g.n_rows // rbig) < 148 * 32 * groups:
+    if _small_graph(g.n_rows, d):
         return f"spmm_chunk_kernel<{d},{mode},4-row chunks>"
     if mode == "adam":
         return f"spmm_chunk_kernel<{d},{mode}>"
