@@ -841,17 +841,20 @@ __global__ void __launch_bounds__(kThreads) spmm_long_combine_kernel(const __gri
     float4 acc[G::VEC];
 #pragma unroll
     for (int v = 0; v < G::VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    // partials are summed in segment order; loads are issued 8 segments ahead of the adds
-    constexpr int CB = 8;
+    // partials are summed in segment order; loads are issued CB segments ahead of the adds and are
+    // unconditional (clamped index): the hottest row's chain of dependent batches is the whole
+    // duration of this kernel on small graphs (Gowalla shape: ~300 segments)
+    constexpr int CB = G::VEC > 1 ? 8 : 16;
     for (int s = s0; s < s1; s += CB) {
         float4 t[CB][G::VEC];
 #pragma unroll
-        for (int k = 0; k < CB; ++k)
-            if (s + k < s1)
+        for (int k = 0; k < CB; ++k) {
+            const int sk = min(s + k, s1 - 1);
 #pragma unroll
-                for (int v = 0; v < G::VEC; ++v)
-                    t[k][v] = *reinterpret_cast<const float4 *>(a.seg_ws + (size_t)(s + k) * D + sub * 4 +
-                                                                 v * G::LANES * 4);
+            for (int v = 0; v < G::VEC; ++v)
+                t[k][v] = *reinterpret_cast<const float4 *>(a.seg_ws + (size_t)sk * D + sub * 4 +
+                                                             v * G::LANES * 4);
+        }
 #pragma unroll
         for (int k = 0; k < CB; ++k)
             if (s + k < s1) {
