@@ -35,6 +35,12 @@ constexpr int kUnroll = 8;
 #ifndef LGCN_SPMM_MINBLOCKS_LIGHT
 #define LGCN_SPMM_MINBLOCKS_LIGHT 1    // (8 = cap at 64 registers: measured slower, 7.02 vs 6.47 ms)
 #endif
+#ifndef LGCN_SPMM_MINBLOCKS_SMALL_MEAN
+#define LGCN_SPMM_MINBLOCKS_SMALL_MEAN 6    // (the MEAN epilogue spills at 64 registers)
+#endif
+#ifndef LGCN_SPMM_MINBLOCKS_SMALL
+#define LGCN_SPMM_MINBLOCKS_SMALL 8    // small (latency-bound) graphs want the warps: 64 registers,
+#endif                                 // Gowalla step 0.615 -> 0.565 ms (6 blocks: 0.586)
 constexpr int kWarps = LGCN_SPMM_WARPS;
 constexpr int kThreads = kWarps * 32;
 
@@ -250,7 +256,8 @@ __device__ __forceinline__ void long_seg_body(const lgcn_spmm_args &a, int64_t b
 
 // ---- main kernel: one worker per chunk of R rows ---------------------------------------------
 template <int D, int MODE, int RSEL, bool HINT, bool XF>
-__global__ void __launch_bounds__(kThreads, (MODE == LGCN_SPMM_PLAIN || MODE == LGCN_SPMM_ADD) ? LGCN_SPMM_MINBLOCKS_LIGHT : LGCN_SPMM_MINBLOCKS)
+__global__ void __launch_bounds__(kThreads, RSEL == 1 ? (MODE == LGCN_SPMM_MEAN ? LGCN_SPMM_MINBLOCKS_SMALL_MEAN : LGCN_SPMM_MINBLOCKS_SMALL) :
+                                  (MODE == LGCN_SPMM_PLAIN || MODE == LGCN_SPMM_ADD) ? LGCN_SPMM_MINBLOCKS_LIGHT : LGCN_SPMM_MINBLOCKS)
 spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
     using G = RowGeom<D>;
     using C = ChunkCfg<D, RSEL>;
