@@ -184,24 +184,17 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line.  NCCL prints its version banner on the C-level stdout
+    # of whichever rank brings a communicator up, so for the whole run fd 1 points at stderr and
+    # the result line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL prints its version banner to the C-level
-        # stdout when the communicator comes up, so fd 1 points at stderr until that is done
-        import ctypes
-        sys.stdout.flush()
-        saved_fd = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            dist.all_reduce(torch.zeros(1, device=dev))
-            torch.cuda.synchronize()
-        finally:
-            ctypes.CDLL(None).fflush(None)
-            os.dup2(saved_fd, 1)
-            os.close(saved_fd)
+        dist.init_process_group("nccl", device_id=dev)
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
 
@@ -397,9 +390,10 @@ def run_b200(args):
             "roofline": roofline, "kernels": kernels, "eval": ev, "cpu_baseline": cpu,
             "loss": last_loss,
         }
-        print(json.dumps(line), flush=True)
+        os.write(out_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+    os.close(out_fd)
 
 
 def main():
