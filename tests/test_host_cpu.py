@@ -175,6 +175,26 @@ def test_engine_checkpoint_is_reference_format():
         eng2.load_state_dict(bad)
 
 
+def test_bench_reference_arm_prints_one_contract_line():
+    """``bench.py --impl reference`` (the reference's CPU path on the host cores) prints exactly
+    one JSON line with the contract's keys; it needs no GPU."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                        "--workload", "tiny", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "lightgcn_epoch_s" and d["unit"] == "s"
+    assert d["higher_is_better"] is False and d["value"] > 0 and d["steps"] == 2
+    assert d["config"]["workload"] == "tiny"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
 def test_mask_csr_matches_groupby_lists():
     from gcn_recommendation_b200.engine import build_mask_csr
     tu = np.array([3, 1, 3, 0, 1, 3], np.int64)
