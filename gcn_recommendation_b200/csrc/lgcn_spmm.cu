@@ -788,6 +788,47 @@ __device__ __forceinline__ void long_seg_body(const lgcn_spmm_args &a, int64_t b
 #pragma unroll
     for (int v = 0; v < G::VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int2 *cvp = reinterpret_cast<const int2 *>(a.long_colval) + beg;
+    if (a.x_rowflag) {
+        // flagged input (the sparse backward hops): one flag byte per lane for the whole tile, a
+        // ballot of the live entries, and only those are gathered and summed -- in stream order,
+        // so the partial sum is bit-equal to the dense walk (a dead entry adds w * 0)
+        const int gshift = grp * G::LANES;
+        const unsigned gbits = (G::LANES == 32) ? 0xffffffffu : ((1u << G::LANES) - 1u);
+        for (int base = 0; base < maxdeg; base += G::LANES) {
+            int2 cv = make_int2(0, 0);
+            unsigned fl = 0;
+            if (base + sub < deg) {
+                cv = __ldg(cvp + base + sub);
+                fl = __ldg(a.x_rowflag + cv.x);
+            }
+            unsigned lm = (__ballot_sync(0xffffffffu, fl != 0) >> gshift) & gbits;
+            while (__any_sync(0xffffffffu, lm != 0)) {
+                float4 x[kUnroll][G::VEC];
+                unsigned m = lm;
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const bool on = m != 0;
+                    const int j = on ? __ffs(m) - 1 : 0;
+                    m &= m - 1;
+                    const int cj = __shfl_sync(0xffffffffu, cv.x, j, G::LANES);
+                    const float *src = on ? a.x + (size_t)cj * D + sub * 4 : a.zero_row + sub * 4;
+#pragma unroll
+                    for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
+                }
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const bool on = lm != 0;
+                    const int j = on ? __ffs(lm) - 1 : 0;
+                    lm &= lm - 1;
+                    const float wj = __int_as_float(__shfl_sync(0xffffffffu, cv.y, j, G::LANES));
+                    if (on) {
+#pragma unroll
+                        for (int v = 0; v < G::VEC; ++v) fma4(acc[v], wj, x[u][v]);
+                    }
+                }
+            }
+        }
+    } else
     for (int base = 0; base < maxdeg; base += G::LANES) {
         int2 cv = make_int2(0, 0);
         if (base + sub < deg) cv = __ldg(cvp + base + sub);
@@ -799,16 +840,10 @@ __device__ __forceinline__ void long_seg_body(const lgcn_spmm_args &a, int64_t b
             for (int u = 0; u < kUnroll; ++u)
 #pragma unroll
                 for (int v = 0; v < G::VEC; ++v) x[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-            int cjs[kUnroll];
-            unsigned xfl[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                cjs[u] = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
-                xfl[u] = a.x_rowflag ? (unsigned)__ldg(a.x_rowflag + cjs[u]) : 1u;
-            }
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const float *src = xfl[u] ? a.x + (size_t)cjs[u] * D + sub * 4 : a.zero_row + sub * 4;
+                const int cj = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
+                const float *src = a.x + (size_t)cj * D + sub * 4;
 #pragma unroll
                 for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
             }
