@@ -70,11 +70,22 @@ def _batches(rng, tu, ti, num_items, bs, n_steps):
     return out
 
 
-def run_case(main, model_cls, name, shape, d, K, bs, n_steps, use_brand, fusion, seed):
+def run_case(main, model_cls, name, shape, d, K, bs, n_steps, use_brand, fusion, seed,
+             min_degree=3, n_dup=0):
+    """``min_degree=2`` leaves users without any training edge after the test / validation
+    hold-outs (isolated nodes: degree 0 -> d = 0, reference main.py:329); ``n_dup`` appends
+    repeated (user, item) rows to train.parquet (multiplicity > 1 in the adjacency, summed by the
+    reference's COO -> CSR conversion, main.py:321-331)."""
     import torch
 
     torch.set_num_threads(1)
-    inter = synth.generate(shape, seed=seed)
+    inter = synth.generate(shape, seed=seed, min_degree=min_degree)
+    if n_dup:
+        rng_d = np.random.default_rng(seed + 99)
+        pick = rng_d.choice(len(inter.train_user), n_dup, replace=False)
+        pick = np.concatenate([pick, pick[: n_dup // 4]])          # some pairs three times
+        inter.train_user = np.concatenate([inter.train_user, inter.train_user[pick]])
+        inter.train_item = np.concatenate([inter.train_item, inter.train_item[pick]])
     content = synth.side_embeddings(inter.num_items, 768, seed + 1) if fusion else None
     golden = {}
     with tempfile.TemporaryDirectory() as tmp:
@@ -187,6 +198,9 @@ def main_():
     run_case(main, lg.LightGCN, "tiny_lightgcn_d128_k4", "tiny", 128, 4, 256, 3, False, False, 1)
     run_case(main, lg.LightGCN, "tiny_lightgcn_brand_d64_k3", "tiny", 64, 3, 256, 3, True, False, 2)
     run_case(main, lf.LightGCN_Fusion, "tiny_fusion_d64_k3", "tiny", 64, 3, 256, 4, False, True, 3)
+    # edge cases (oracle-only): isolated users, repeated interactions, a single layer, d = 32
+    run_case(main, lg.LightGCN, "tiny_edge_d32_k1", "tiny", 32, 1, 64, 3, False, False, 4,
+             min_degree=2, n_dup=40)
 
 
 if __name__ == "__main__":

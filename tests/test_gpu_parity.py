@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = 1e-5
 CASES = ["tiny_lightgcn_d64_k3", "tiny_lightgcn_d128_k4", "tiny_lightgcn_brand_d64_k3",
-         "tiny_fusion_d64_k3"]
+         "tiny_fusion_d64_k3", "tiny_edge_d32_k1"]
 
 
 @pytest.fixture(scope="module")
@@ -59,7 +59,7 @@ def test_csr_build_bit_exact(golden, dev, case):
     assert np.array_equal(_bits(csr.val.cpu().numpy()), _bits(g["adj_val"]))
 
 
-@pytest.mark.parametrize("case", CASES[:1] + CASES[2:3])
+@pytest.mark.parametrize("case", CASES[:1] + CASES[2:3] + CASES[4:])
 def test_csr_from_reference_coo_tensor(golden, dev, case):
     from gcn_recommendation_b200.graph import NormAdjCSR, csr_for
     g = golden(case)
@@ -246,7 +246,7 @@ def test_spmm_long_row_plan_within_tolerance(dev, d):
     assert mx < TOL and fro < TOL
 
 
-@pytest.mark.parametrize("case", CASES[:3])
+@pytest.mark.parametrize("case", CASES[:3] + CASES[4:])
 def test_propagate_bit_exact_vs_reference(golden, dev, case):
     from gcn_recommendation_b200 import ops
     g = golden(case)

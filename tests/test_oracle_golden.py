@@ -11,8 +11,10 @@ import pytest
 from conftest import rel_err
 from oracle import lgcn_oracle as orc
 
+# tiny_edge_d32_k1: users without any training edge (degree 0), repeated interactions
+# (multiplicity 2 and 3 in the adjacency), a single layer, d = 32
 CASES = ["tiny_lightgcn_d64_k3", "tiny_lightgcn_d128_k4", "tiny_lightgcn_brand_d64_k3",
-         "tiny_fusion_d64_k3"]
+         "tiny_fusion_d64_k3", "tiny_edge_d32_k1"]
 TOL = 1e-5
 
 
