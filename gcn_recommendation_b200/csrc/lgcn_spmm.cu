@@ -962,13 +962,19 @@ static int launch_ring(const lgcn_spmm_args &a, cudaStream_t st) {
     return 0;
 }
 
+// small graphs: 4-row chunks so that the chip is filled (>= ~2 waves of workers), and the long-row
+// segment workers ride in the chunk launch
+template <int D>
+static bool small_graph(int64_t n_rows, int32_t flags) {
+    const int64_t big_workers = n_rows / ChunkCfg<D, 0>::R;
+    return big_workers < (int64_t)kNumSMs * 32 * RowGeom<D>::GROUPS && !(flags & LGCN_SPMM_F_BIG_PATH);
+}
+
 template <int D, int MODE>
 static int launch_mode(const lgcn_spmm_args &a, cudaStream_t st) {
     using G = RowGeom<D>;
     constexpr int groups_per_block = kWarps * G::GROUPS;
-    // small graphs: 4-row chunks so that the chip is filled (>= ~2 waves of workers)
-    const int64_t big_workers = a.n_rows / ChunkCfg<D, 0>::R;
-    const bool small = big_workers < (int64_t)kNumSMs * 32 * G::GROUPS && !(a.flags & LGCN_SPMM_F_BIG_PATH);
+    const bool small = small_graph<D>(a.n_rows, a.flags);
     if (a.n_long > 0 && !(small && a.n_rows > 0)) {     // small graphs: inside the chunk launch
         const unsigned gs = (unsigned)((a.n_seg + groups_per_block - 1) / groups_per_block);
         spmm_long_seg_kernel<D><<<gs, kThreads, 0, st>>>(a);
@@ -1055,3 +1061,21 @@ extern "C" int lgcn_spmm(const lgcn_spmm_args *args, lgcn_stream_t stream) {
 }
 
 extern "C" size_t lgcn_sizeof_spmm_args(void) { return sizeof(lgcn_spmm_args); }
+
+extern "C" int lgcn_spmm_launches(int64_t n_rows, int32_t d, int32_t n_long, int32_t flags,
+                                  int32_t *small_path) {
+    using namespace lgcn;
+    if (!dim_supported(d)) return LGCN_E_BAD_DIM;
+    if (n_rows < 0 || n_long < 0) return LGCN_E_BAD_ARG;
+    bool small = false;
+    switch (d) {
+        case 16:  small = small_graph<16>(n_rows, flags); break;
+        case 32:  small = small_graph<32>(n_rows, flags); break;
+        case 64:  small = small_graph<64>(n_rows, flags); break;
+        case 128: small = small_graph<128>(n_rows, flags); break;
+        case 256: small = small_graph<256>(n_rows, flags); break;
+    }
+    if (small_path) *small_path = small ? 1 : 0;
+    if (n_long == 0) return 1;                 // main kernel only
+    return small ? 2 : 3;                      // (+ segments) + combine
+}

@@ -28,20 +28,24 @@ HOT_BYTES = int(float(os.environ.get("LGCN_HOT_MB", "32")) * (1 << 20))
 SPMM_FLAGS_EXTRA = int(os.environ.get("LGCN_SPMM_FLAGS", "0"))           # OR-ed into lgcn_spmm_args.flags (tests / A-B measurements force a kernel)
 
 
+def _spmm_plan(n_rows, d, n_long):
+    """(kernel launches per ``lgcn_spmm`` call, small-graph path?) as the library itself decides
+    (host-only query, csrc/lgcn_spmm.cu ``launch_mode``)."""
+    small = ctypes.c_int32(0)
+    n = _lib.load().lgcn_spmm_launches(int(n_rows), int(d), int(n_long), int(SPMM_FLAGS_EXTRA),
+                                       ctypes.byref(small))
+    if n <= 0:
+        check(n)
+    return n, bool(small.value)
+
+
 def _small_graph(n_rows, d):
-    """Mirror of the kernel selection in csrc/lgcn_spmm.cu ``launch_mode``: graphs with too few
-    16-row chunks to fill the chip run 4-row chunks (and carry the long-row segment workers in
-    the same launch)."""
-    lanes = min(32, d // 4)
-    rbig = min(lanes, max(4, 2048 // d))
-    return (n_rows // rbig) < 148 * 32 * (32 // lanes) and not (SPMM_FLAGS_EXTRA & _lib.SPMM_F_BIG_PATH)
+    return _spmm_plan(n_rows, d, 0)[1]
 
 
 def spmm_launches(g, d):
     """Kernels one ``lgcn_spmm`` call launches for this graph / width."""
-    if g.n_long == 0:
-        return 1
-    return 2 if _small_graph(g.n_rows, d) else 3
+    return _spmm_plan(g.n_rows, d, g.n_long)[0]
 
 
 def _launch_spmm(a, g, dev, tag):

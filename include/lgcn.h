@@ -157,6 +157,13 @@ typedef struct lgcn_spmm_args {
 LGCN_API int lgcn_spmm(const lgcn_spmm_args *args_host, lgcn_stream_t stream);
 /* sizeof(lgcn_spmm_args) as compiled, so that a binding can verify its struct layout */
 LGCN_API size_t lgcn_sizeof_spmm_args(void);
+/* Host-only query (launches nothing): how many kernels one lgcn_spmm call launches for a graph of
+ * n_rows rows with n_long long rows at width d under `flags` (1 = main kernel; with long rows
+ * 3 = segments + main + combine, or 2 on small graphs whose segment workers ride in the main
+ * launch).  *small_path (optional) = 1 when the small-graph 4-row-chunk path is taken.  Returns
+ * the count (> 0) or a negative LGCN_E_* code. */
+LGCN_API int lgcn_spmm_launches(int64_t n_rows, int32_t d, int32_t n_long, int32_t flags,
+                       int32_t *small_path);
 
 /* ---------------------------------------------------------------------------------------
  * a4  Fused BPR + L2 step.

@@ -29,6 +29,23 @@ def test_abi_exports_every_declared_symbol():
     assert b"embedding dim" in lib.lgcn_error_string(-1)
 
 
+def test_spmm_plan_query_matches_documented_selection():
+    """``lgcn_spmm_launches`` (host-only): Gowalla shape -> small path, 2 launches with long rows;
+    Amazon shape -> large-graph kernels, 3 launches, at every sharded width."""
+    from gcn_recommendation_b200 import _lib, ops
+    assert ops._spmm_plan(70_840, 64, 0) == (1, True)
+    assert ops._spmm_plan(70_840, 64, 1600) == (2, True)
+    for d in (16, 32, 64, 128):
+        assert ops._spmm_plan(14_700_001, d, 2749) == (3, False)
+    old = ops.SPMM_FLAGS_EXTRA
+    ops.SPMM_FLAGS_EXTRA = _lib.SPMM_F_BIG_PATH
+    try:
+        assert ops._spmm_plan(7006, 64, 10) == (3, False)
+    finally:
+        ops.SPMM_FLAGS_EXTRA = old
+    assert _lib.load().lgcn_spmm_launches(10, 48, 0, 0, None) == -1
+
+
 def test_argument_errors_are_reported_not_thrown():
     from gcn_recommendation_b200 import _lib
     lib = _lib.load()
