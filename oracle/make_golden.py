@@ -191,9 +191,104 @@ def run_case(main, model_cls, name, shape, d, K, bs, n_steps, use_brand, fusion,
           f"({os.path.getsize(out) / 1024:.0f} KiB)")
 
 
+def _digest(a):
+    """fp64 (sum, sum of squares) of an array: a compact witness of a large tensor."""
+    a = np.asarray(a, np.float64)
+    return np.asarray([a.sum(), (a * a).sum()], np.float64)
+
+
+def run_config_scale_case(main, model_cls, name, shape, d, K, bs, n_steps, seed, sample_rows=256):
+    """BASELINE.json configs[1] scale (the Gowalla-shape graph): ``n_steps`` recorded steps of the
+    reference's own loop (reference main.py:488-531) followed by ``main.evaluate`` (main.py:404-439)
+    over ALL validation users.  Inputs regenerate from ``synth.generate(shape, seed)`` and
+    ``torch.manual_seed(42)``, so only the outputs are stored: the loss curve, the recorded batch
+    stream (int32), the top-20 ids + scores of every validation user, recall / NDCG, and fp64
+    digests + a row sample of the large tensors (adjacency, init / final parameters, final F)."""
+    import torch
+
+    torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
+    inter = synth.generate(shape, seed=seed)
+    golden = dict(shape=np.asarray(shape), seed=seed, d=d, K=K, bs=bs, lam=1e-4, lr=1e-3,
+                  num_users=inter.num_users, num_items=inter.num_items, num_brands=inter.num_brands)
+    with tempfile.TemporaryDirectory() as tmp:
+        ddir = os.path.join(tmp, "processed")
+        synth.write_reference_format(inter, ddir, None)
+        dev = torch.device("cpu")
+        (train_df, val_df, test_df, U, I, B, adj, _) = main.load_preprocessed_data(
+            ddir, dev, use_brand=False, debug=False)
+    tu, ti = train_df["user_idx"].values, train_df["item_idx"].values
+    golden.update(n_train=len(tu), n_val=len(val_df), nnz=int(adj._nnz()),
+                  adj_val_digest=_digest(adj._values().numpy()),
+                  adj_col_digest=_digest(adj._indices()[1].numpy()),
+                  train_digest=_digest(tu * I + ti),
+                  val_digest=_digest(val_df["user_idx"].values * I + val_df["item_idx"].values))
+    cfg = types.SimpleNamespace(embedding_dim=d, n_layers=K, debug=False, device=dev,
+                                learning_rate=1e-3, weight_decay=1e-4, top_k=20, batch_size=bs)
+    main.config = cfg
+    torch.manual_seed(42)                                     # reference main.py:607
+    model = model_cls(U, I, B, cfg).to(dev)
+    rows = np.random.default_rng(seed + 3).choice(min(U, I), sample_rows, replace=False)
+    golden["sample_rows"] = rows
+    for k, v in model.state_dict().items():
+        golden["init_digest/" + k] = _digest(v.numpy())
+    opt = torch.optim.Adam(model.parameters(), lr=cfg.learning_rate)   # main.py:469
+    with torch.no_grad():
+        fu, fi, fb, _, _ = model(adj, use_brand=False)
+        golden["fwd_digest/user"], golden["fwd_digest/item"] = _digest(fu.numpy()), _digest(fi.numpy())
+        golden["fwd_sample/user"], golden["fwd_sample/item"] = fu.numpy()[rows].copy(), fi.numpy()[rows].copy()
+    rng = np.random.default_rng(seed + 7)
+    batches = _batches(rng, tu, ti, I, bs, n_steps)
+    losses = []
+    model.train()
+    for s, (u, p, n) in enumerate(batches):                   # main.py:488-531
+        users, pos, neg = torch.from_numpy(u), torch.from_numpy(p), torch.from_numpy(n)
+        opt.zero_grad()
+        fu, fi, fb, u0, i0 = model(adj, use_brand=False)
+        loss = main.bpr_loss_reg(fu[users], fi[pos], fi[neg], u0[users], i0[pos], i0[neg],
+                                 cfg.weight_decay)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+        print(f"  step {s}: loss {losses[-1]:.6f}", flush=True)
+    golden["losses"] = np.asarray(losses, np.float64)
+    golden["batch_users"] = np.stack([b[0] for b in batches]).astype(np.int32)
+    golden["batch_pos"] = np.stack([b[1] for b in batches]).astype(np.int32)
+    golden["batch_neg"] = np.stack([b[2] for b in batches]).astype(np.int32)
+    for k, v in model.state_dict().items():
+        golden["final_digest/" + k] = _digest(v.numpy())
+        golden["final_sample/" + k] = v.numpy()[rows % v.shape[0]].copy()
+
+    rec = []
+    real_topk = torch.topk
+
+    def spy(*a, **kw):
+        out = real_topk(*a, **kw)
+        rec.append((out[0].numpy().copy(), out[1].numpy().copy()))
+        return out
+
+    with mock.patch.object(torch, "topk", spy), mock.patch.object(main, "tqdm", lambda x, **k: x):
+        recall, ndcg = main.evaluate(model, val_df, train_df, adj, 20, dev, use_brand=False)
+    golden["eval/recall"] = np.float64(recall)
+    golden["eval/ndcg"] = np.float64(ndcg)
+    golden["eval/topk_scores"] = np.concatenate([r[0] for r in rec])
+    golden["eval/topk_ids"] = np.concatenate([r[1] for r in rec]).astype(np.int32)
+    golden["eval/users"] = np.asarray(list(dict(zip(val_df["user_idx"], val_df["item_idx"])).keys()),
+                                      np.int32)
+    with torch.no_grad():
+        fu, fi, _, _, _ = model(adj)
+        golden["evalF_digest/user"], golden["evalF_digest/item"] = _digest(fu.numpy()), _digest(fi.numpy())
+    out = os.path.join(REPO, "tests", "golden", name + ".npz")
+    np.savez_compressed(out, **golden)
+    print(f"wrote {out}: recall@20={recall:.6f} ndcg@20={ndcg:.6f} loss[0]={losses[0]:.6f} "
+          f"loss[-1]={losses[-1]:.6f} ({os.path.getsize(out) / 1024:.0f} KiB)")
+
+
 def main_():
     main, lg, lf = _import_reference()
     os.makedirs(os.path.join(REPO, "tests", "golden"), exist_ok=True)
+    if "--config-scale" in sys.argv:       # ~2 min of CPU: the Gowalla-shape run (configs[1])
+        run_config_scale_case(main, lg.LightGCN, "gowalla_lightgcn_d64_k3", "gowalla", 64, 3, 2048, 20, 0)
+        return
     run_case(main, lg.LightGCN, "tiny_lightgcn_d64_k3", "tiny", 64, 3, 256, 6, False, False, 0)
     run_case(main, lg.LightGCN, "tiny_lightgcn_d128_k4", "tiny", 128, 4, 256, 3, False, False, 1)
     run_case(main, lg.LightGCN, "tiny_lightgcn_brand_d64_k3", "tiny", 64, 3, 256, 3, True, False, 2)

@@ -16,6 +16,16 @@ workload = sys.argv[1] if len(sys.argv) > 1 else "amazon"
 mode = sys.argv[2] if len(sys.argv) > 2 else "plain"
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 dev = torch.device("cuda:0")
+if os.environ.get("LGCN_L2_FETCH"):
+    # experiment: device-wide L2 fetch granularity (cudaLimitMaxL2FetchGranularity
+    # = 0x05; 32 / 64 / 128 bytes) -- narrow (64-byte) rows pay a 128-byte DRAM fetch by default
+    import ctypes
+    torch.zeros(1, device=dev)
+    rt = ctypes.CDLL("/usr/local/cuda/lib64/libcudart.so")
+    rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ["LGCN_L2_FETCH"])))
+    val = ctypes.c_size_t(0)
+    rt.cudaDeviceGetLimit(ctypes.byref(val), 5)
+    print(f"cudaLimitMaxL2FetchGranularity <- {os.environ['LGCN_L2_FETCH']}: rc={rc}, now {val.value}")
 # LGCN_SPMM_FLAGS (read by ops): 2 = chunk kernel instead of ring, 16 = ring for the ADAM epilogue too
 U, I, B, total, d, K = synth.SHAPES[workload]
 if len(sys.argv) > 4:

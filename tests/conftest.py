@@ -37,3 +37,46 @@ def rel_err(a, b):
     den = max(float(np.abs(b).max()), 1e-30)
     fro = float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
     return float(np.abs(a - b).max() / den), fro
+
+
+def digest(a):
+    """fp64 (sum, sum of squares): the compact witness oracle/make_golden.py stores for big tensors."""
+    import numpy as np
+
+    a = np.asarray(a, np.float64)
+    return np.asarray([a.sum(), (a * a).sum()], np.float64)
+
+
+def config_scale_inputs(g):
+    """Regenerate the inputs of the config-scale golden (synth + seed) and check them against the
+    stored digests.  Returns (inter, tu, ti, vu, vi)."""
+    import numpy as np
+
+    from gcn_recommendation_b200 import synth
+    inter = synth.generate(str(g["shape"]), seed=int(g["seed"]))
+    tu, ti, vu, vi = inter.split_validation()
+    I = inter.num_items
+    assert len(tu) == int(g["n_train"]) and len(vu) == int(g["n_val"])
+    assert np.array_equal(digest(tu * I + ti), g["train_digest"])
+    assert np.array_equal(digest(vu * I + vi), g["val_digest"])
+    return inter, tu, ti, vu, vi
+
+
+def near_tie_rows_ok(ids, ref_ids, ref_sc, tol=2e-6):
+    """Rows whose ids differ from the reference's torch.topk must differ only inside fp32
+    near-ties: at every differing position the reference's score has a neighbour (or the cut-off
+    at rank k) within ``tol`` relative.  Returns the number of differing rows."""
+    import numpy as np
+
+    bad_rows = np.where((ids != ref_ids).any(1))[0]
+    for r in bad_rows:
+        s = ref_sc[r].astype(np.float64)
+        scale = np.abs(s).max()
+        for j in np.where(ids[r] != ref_ids[r])[0]:
+            near = j == len(s) - 1                       # swap across the rank-k cut-off
+            if j > 0:
+                near |= abs(s[j] - s[j - 1]) <= tol * scale
+            if j + 1 < len(s):
+                near |= abs(s[j] - s[j + 1]) <= tol * scale
+            assert near, f"user row {r}: id mismatch at rank {j} without a near-tie"
+    return len(bad_rows)

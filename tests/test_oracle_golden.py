@@ -8,7 +8,7 @@ bit-exact too (sequential FMA); loss / grads / Adam within 1e-5 relative.
 import numpy as np
 import pytest
 
-from conftest import rel_err
+from conftest import config_scale_inputs, digest as _digest, near_tie_rows_ok, rel_err
 from oracle import lgcn_oracle as orc
 
 # tiny_edge_d32_k1: users without any training edge (degree 0), repeated interactions
@@ -203,3 +203,69 @@ def test_torch_port_tracks_reference(golden, case):
     rec, ndcg = port.evaluate(users, targets, lists, 20)
     assert rec == pytest.approx(float(g["eval/recall"]), abs=1e-12)
     assert ndcg == pytest.approx(float(g["eval/ndcg"]), abs=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[1] scale: the Gowalla-shape run of the unmodified reference
+# (oracle/make_golden.py --config-scale: 20 recorded steps of main.py:488-531 + main.evaluate)
+# ---------------------------------------------------------------------------------------------
+CONFIG_GOLDEN = "gowalla_lightgcn_d64_k3"
+
+
+def test_config_scale_golden_pins_the_oracle(golden):
+    """The oracle at the full Gowalla shape against the reference's own run: adjacency digests,
+    seed-identical init, bit-exact forward rows, the 20-step loss curve (2e-5), final parameters
+    (1e-5 Frobenius on the sampled rows / digests) and the top-20 of a user sample."""
+    import types
+
+    import torch
+
+    from models.lightgcn import LightGCN
+    g = golden(CONFIG_GOLDEN)
+    inter, tu, ti, vu, vi = config_scale_inputs(g)
+    U, I, B, d, K = inter.num_users, inter.num_items, inter.num_brands, int(g["d"]), int(g["K"])
+    a = orc.build_norm_adj(tu, ti, U, I, B)
+    assert len(a["col"]) == int(g["nnz"])
+    assert np.array_equal(_digest(a["val"]), g["adj_val_digest"])
+    assert np.array_equal(_digest(a["col"]), g["adj_col_digest"])
+    torch.manual_seed(42)
+    m = LightGCN(U, I, B, types.SimpleNamespace(embedding_dim=d, n_layers=K, debug=False))
+    sd = {k: v.detach().numpy().copy() for k, v in m.state_dict().items()}
+    for k, v in sd.items():
+        assert np.array_equal(_digest(v), g["init_digest/" + k]), k
+    P = {k: sd[k] for k in ("user_embedding.weight", "item_embedding.weight", "brand_embedding.weight")}
+    rows = g["sample_rows"]
+    E0 = np.concatenate([P["user_embedding.weight"], P["item_embedding.weight"], P["brand_embedding.weight"]], 0)
+    F, _ = orc.propagate(a["rowptr"], a["col"], a["val"], E0, K)
+    assert np.array_equal(F[:U][rows].view(np.uint32), g["fwd_sample/user"].view(np.uint32))
+    assert np.array_equal(F[U:U + I][rows].view(np.uint32), g["fwd_sample/item"].view(np.uint32))
+    M = {k: np.zeros_like(v) for k, v in P.items()}
+    V = {k: np.zeros_like(v) for k, v in P.items()}
+    for s in range(len(g["losses"])):
+        E0 = np.concatenate([P["user_embedding.weight"], P["item_embedding.weight"], P["brand_embedding.weight"]], 0)
+        F, _ = orc.propagate(a["rowptr"], a["col"], a["val"], E0, K)
+        loss, gF, gU, gI = orc.bpr_loss(F, P["user_embedding.weight"], P["item_embedding.weight"],
+                                        g["batch_users"][s], g["batch_pos"][s], g["batch_neg"][s], U,
+                                        float(g["lam"]))
+        assert abs(loss - g["losses"][s]) <= 2e-5 * abs(g["losses"][s]), (s, loss, g["losses"][s])
+        dE0 = orc.propagate_backward(a["rowptr"], a["col"], a["val"], gF, K)
+        G = {"user_embedding.weight": dE0[:U] + gU, "item_embedding.weight": dE0[U:U + I] + gI,
+             "brand_embedding.weight": dE0[U + I:]}
+        for k in P:
+            orc.adam_step(P[k], G[k], M[k], V[k], s + 1, lr=float(g["lr"]))
+    for k in P:
+        ref = g["final_sample/" + k]
+        mx, fro = rel_err(P[k][rows % P[k].shape[0]], ref)
+        assert fro < 1e-5 and mx < 1e-3, (k, mx, fro)
+        dg = _digest(P[k])
+        assert np.allclose(dg, g["final_digest/" + k], rtol=1e-5, atol=1e-9), k
+    # top-20 of the first 384 validation users from the oracle's own final table
+    E0 = np.concatenate([P["user_embedding.weight"], P["item_embedding.weight"], P["brand_embedding.weight"]], 0)
+    F, _ = orc.propagate(a["rowptr"], a["col"], a["val"], E0, K)
+    users, targets = orc.eval_pairs(vu, vi)
+    assert np.array_equal(users, g["eval/users"])
+    n = 384
+    mr, mc = orc.mask_csr(users[:n], tu, ti, U)
+    ids, sc = orc.score_topk(F[:U], F[U:U + I], users[:n], mr, mc, 20)
+    assert np.allclose(sc, g["eval/topk_scores"][:n], rtol=2e-5, atol=1e-9)
+    assert near_tie_rows_ok(ids, g["eval/topk_ids"][:n], g["eval/topk_scores"][:n]) <= n // 50
