@@ -22,7 +22,7 @@ SPMM_F_BIG_PATH = 4
 SPMM_F_COLD_FIRST = 8
 SPMM_F_FORCE_RING = 16
 BPR_GP_INCLUDES_GF, BPR_NO_GRAD = 1, 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class SpmmArgs(ctypes.Structure):
@@ -43,11 +43,14 @@ class SpmmArgs(ctypes.Structure):
 _SIGNATURES = {
     "lgcn_abi_version": (ctypes.c_int, []),
     "lgcn_error_string": (ctypes.c_char_p, [ctypes.c_int]),
-    "lgcn_csr_from_sorted_coo": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "lgcn_csr_from_sorted_coo": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "lgcn_check_indices": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "lgcn_edge_weights": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "lgcn_spmm": (ctypes.c_int, [ctypes.POINTER(SpmmArgs), c_vp]),
     "lgcn_sizeof_spmm_args": (ctypes.c_size_t, []),
     "lgcn_spmm_launches": (ctypes.c_int, [c_i64, c_i32, c_i32, c_i32, ctypes.POINTER(ctypes.c_int32)]),
+    "lgcn_spmm_kernel_name": (ctypes.c_int, [c_i64, c_i32, c_i32, c_i32, c_i32, ctypes.c_char_p,
+                                             ctypes.c_size_t]),
     "lgcn_bpr_fused": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_f32,
                                       c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "lgcn_bpr_partial": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp]),
@@ -67,6 +70,7 @@ _SIGNATURES = {
     "lgcn_score_topk": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_i32,
                                        c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "lgcn_score_tc_workspace": (ctypes.c_size_t, [c_i64, c_i64, c_i32]),
+    "lgcn_score_tc_launches": (ctypes.c_int, [c_i64, c_i64]),
     "lgcn_score_tc_prepare": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, ctypes.c_size_t, c_vp]),
     "lgcn_score_tc_topk": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_i32,
                                           c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),

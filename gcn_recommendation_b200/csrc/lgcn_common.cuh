@@ -3,12 +3,33 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "lgcn.h"
 
 #define LGCN_LAUNCH_CHECK()                         \
     do {                                            \
         cudaError_t e__ = cudaGetLastError();       \
         if (e__ != cudaSuccess) return (int)e__;    \
+    } while (0)
+
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute is per DEVICE (and
+// context), so the "done" cache is a bit per device ordinal; a race between host threads only
+// repeats the idempotent call.  Use inside a function returning int (0 = ok).  Wrap a kernel name
+// that contains commas in parentheses.
+#define LGCN_OPT_IN_SMEM(kernel, bytes)                                                         \
+    do {                                                                                        \
+        static std::atomic<unsigned long long> done__{0ull};                                    \
+        int dev__ = 0;                                                                          \
+        cudaError_t e__ = cudaGetDevice(&dev__);                                                \
+        if (e__ != cudaSuccess) return (int)e__;                                                \
+        const unsigned long long bit__ = 1ull << (dev__ & 63);                                  \
+        if (!(done__.load(std::memory_order_acquire) & bit__)) {                                \
+            e__ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                       (int)(bytes));                                           \
+            if (e__ != cudaSuccess) return (int)e__;                                            \
+            done__.fetch_or(bit__, std::memory_order_release);                                  \
+        }                                                                                       \
     } while (0)
 
 namespace lgcn {

@@ -290,13 +290,7 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
 template <int D>
 int launch_fwd(const float *Eid, const float *C, const float *W, const float *b, int64_t n_items, int c,
                float *H, cudaStream_t st) {
-    static bool done = false;
-    if (!done) {
-        cudaError_t e = cudaFuncSetAttribute(fusion_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(Smem<D>));
-        if (e != cudaSuccess) return (int)e;
-        done = true;
-    }
+    LGCN_OPT_IN_SMEM((fusion_fwd_tc_kernel<D>), sizeof(Smem<D>));
     const int64_t tiles = (n_items + MT - 1) / MT;
     const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
     fusion_fwd_tc_kernel<D><<<grid, kThreads, sizeof(Smem<D>), st>>>(Eid, C, W, b, n_items, c, H);
@@ -523,13 +517,7 @@ fusion_bwd_w_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ 
 template <int D>
 int launch_bwd_w(const float *Eid, const float *C, const float *H, const float *gH, int64_t n_items,
                  int c, float *gW, float *gb, cudaStream_t st) {
-    static bool done = false;
-    if (!done) {
-        cudaError_t e = cudaFuncSetAttribute(fusion_bwd_w_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(SmemBw<D>));
-        if (e != cudaSuccess) return (int)e;
-        done = true;
-    }
+    LGCN_OPT_IN_SMEM((fusion_bwd_w_tc_kernel<D>), sizeof(SmemBw<D>));
     const int ktiles = (D + c + MT - 1) / MT;
     int64_t slabs = kNumSMs / ktiles;                            // one wave of CTAs (1 CTA per SM)
     if (slabs < 1) slabs = 1;

@@ -7,10 +7,23 @@
 
 namespace lgcn {
 
+// status[0] += number of idx[i] outside [lo, hi): the IndexError the reference's gathers raise
+// (reference main.py:496-497 index the model outputs with the batch) as a device-side count.
+__global__ void check_indices_kernel(const int64_t *__restrict__ idx, int64_t n, int64_t lo, int64_t hi,
+                                     int32_t *__restrict__ status) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t v = idx[i];
+        bad += (v < lo || v >= hi) ? 1 : 0;
+    }
+    if (bad) atomicAdd(status, bad);
+}
+
 // rowptr[r] = first e with coo_row[e] >= r.  One thread per entry boundary.
 __global__ void csr_from_sorted_coo_kernel(const int64_t *__restrict__ row,
                                            const int64_t *__restrict__ colin, int64_t nnz,
-                                           int64_t n_rows, int32_t *__restrict__ rowptr,
+                                           int64_t n_rows, int64_t n_cols, int32_t *__restrict__ rowptr,
                                            int32_t *__restrict__ col, int32_t *__restrict__ status) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e <= nnz; e += stride) {
@@ -19,7 +32,7 @@ __global__ void csr_from_sorted_coo_kernel(const int64_t *__restrict__ row,
         if (e < nnz) {
             const int64_t c = colin[e];
             col[e] = (int32_t)c;
-            bool bad = r_cur < 0 || r_cur >= n_rows || c < 0 || c > 0x7fffffffLL;
+            bool bad = r_cur < 0 || r_cur >= n_rows || c < 0 || c >= n_cols;
             if (e > 0) bad = bad || r_cur < r_prev || (r_cur == r_prev && c <= colin[e - 1]);
             if (bad) atomicAdd(status, 1);
         }
@@ -46,10 +59,23 @@ __global__ void edge_weights_kernel(const int32_t *__restrict__ rowptr,
 
 }  // namespace lgcn
 
+extern "C" int lgcn_check_indices(const int64_t *idx, int64_t n, int64_t lo, int64_t hi, int32_t *status,
+                                  lgcn_stream_t stream) {
+    if (n < 0 || !status || (n > 0 && !idx)) return LGCN_E_BAD_ARG;
+    if (n == 0) return 0;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    lgcn::check_indices_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        idx, n, lo, hi, status);
+    LGCN_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int lgcn_csr_from_sorted_coo(const int64_t *coo_row, const int64_t *coo_col,
-                                        int64_t nnz, int64_t n_rows, int32_t *rowptr,
+                                        int64_t nnz, int64_t n_rows, int64_t n_cols, int32_t *rowptr,
                                         int32_t *col, int32_t *status, lgcn_stream_t stream) {
-    if (nnz < 0 || n_rows < 0 || !rowptr || !status) return LGCN_E_BAD_ARG;
+    if (nnz < 0 || n_rows < 0 || n_cols < 0 || !rowptr || !status) return LGCN_E_BAD_ARG;
+    if (n_cols > 0x7fffffffLL) return LGCN_E_TOO_LARGE;
     if (nnz > 0 && (!coo_row || !coo_col || !col)) return LGCN_E_BAD_ARG;
     if (nnz > 0x7fffffffLL || n_rows > 0x7fffffffLL) return LGCN_E_TOO_LARGE;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -58,8 +84,8 @@ extern "C" int lgcn_csr_from_sorted_coo(const int64_t *coo_row, const int64_t *c
     const int threads = 256;
     const int64_t blocks = (nnz + 1 + threads - 1) / threads;
     const unsigned grid = (unsigned)(blocks < 148 * 16 ? blocks : 148 * 16);
-    lgcn::csr_from_sorted_coo_kernel<<<grid, threads, 0, st>>>(coo_row, coo_col, nnz, n_rows, rowptr,
-                                                              col, status);
+    lgcn::csr_from_sorted_coo_kernel<<<grid, threads, 0, st>>>(coo_row, coo_col, nnz, n_rows, n_cols,
+                                                              rowptr, col, status);
     LGCN_LAUNCH_CHECK();
     return 0;
 }

@@ -286,13 +286,7 @@ extern "C" int lgcn_score_topk(const float *Fu, const float *Fi, const int64_t *
     if (mask_rowptr && !mask_col) return LGCN_E_BAD_ARG;
     if (n_items > 0x7fffffffLL) return LGCN_E_TOO_LARGE;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(ScoreSmem));
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    LGCN_OPT_IN_SMEM(score_topk_kernel, sizeof(ScoreSmem));
     const int64_t blocks = (nu + TU - 1) / TU;
     if (blocks > 0x7fffffffLL) return LGCN_E_TOO_LARGE;
     int splits = choose_splits(nu, n_items);

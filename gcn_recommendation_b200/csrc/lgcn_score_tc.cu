@@ -213,13 +213,20 @@ template <int D>
 __global__ void __launch_bounds__(kThreads, 1)
 score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ users, int64_t nu,
                     const __nv_bfloat16 *__restrict__ Bt, const float *__restrict__ vnorm,
-                    const float *__restrict__ wnorm, int64_t n_items, int n_tiles,
+                    const float *__restrict__ wnorm, int64_t n_items, int n_tiles_all, int tiles_per_split,
                     const int64_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_col,
                     float *__restrict__ cand_s, int32_t *__restrict__ cand_i, float *__restrict__ tau_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FilterSmem<D> &sm = *reinterpret_cast<FilterSmem<D> *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t q0 = (int64_t)blockIdx.x * MT;
+    // blockIdx.y = item split (few users: the catalogue is cut so that the chip is filled): this
+    // CTA sweeps item tiles [t0, t0 + n_tiles) and keeps its own candidate set per user
+    const int t0 = (int)blockIdx.y * tiles_per_split;
+    const int n_tiles = min(tiles_per_split, n_tiles_all - t0);
+    cand_s += (size_t)blockIdx.y * nu * CAND;
+    cand_i += (size_t)blockIdx.y * nu * CAND;
+    tau_out += (size_t)blockIdx.y * nu * NB;
     constexpr uint32_t TILE_BYTES = NT * D * 2;
     constexpr uint32_t LBO = 16 * 128;     // bytes between K chunks (16 row groups of 128 B)
     constexpr uint32_t SBO = 128;          // bytes between 8-row groups
@@ -268,7 +275,7 @@ score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ us
                 const int s = t % NSTAGE;
                 mbar_wait(smem_u32(&sm.empty[s]), ((t / NSTAGE) & 1) ^ 1);
                 mbar_expect_tx(smem_u32(&sm.full[s]), TILE_BYTES);
-                bulk_g2s(smem_u32(&sm.B[s][0]), Bt + (size_t)t * (NT * D), TILE_BYTES, smem_u32(&sm.full[s]));
+                bulk_g2s(smem_u32(&sm.B[s][0]), Bt + (size_t)(t0 + t) * (NT * D), TILE_BYTES, smem_u32(&sm.full[s]));
             }
         }
     } else if (warp == 1) {
@@ -313,16 +320,16 @@ score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ us
             cu = 1.05f * 0.00390625f * sqrtf(n2) * 1.000001f;
         }
         const float4 *wn4 = reinterpret_cast<const float4 *>(wnorm);
-        float4 wn_next = g < n_tiles ? __ldg(wn4 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 wn_next = g < n_tiles ? __ldg(wn4 + t0 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
         int64_t mb = 0, me = 0;
         if (mask_rowptr && q < nu) { mb = mask_rowptr[q]; me = mask_rowptr[q + 1]; }
         int next_masked = (mb < me) ? __ldg(mask_col + mb) : 0x7fffffff;
         for (int t = g; t < n_tiles; t += NB) {
             const float4 wn_t = wn_next;                   // window norms of this tile, fetched a tile ahead
-            if (t + NB < n_tiles) wn_next = __ldg(wn4 + t + NB);
+            if (t + NB < n_tiles) wn_next = __ldg(wn4 + t0 + t + NB);
             mbar_wait(smem_u32(&sm.tfull[g]), ((t / NB) & 1));
             tc_fence_after();
-            const int tile_item0 = t * NT;
+            const int tile_item0 = (t0 + t) * NT;
             // this group sees every NB-th tile: advance the mask cursor to the tile start
             while (next_masked < tile_item0) {            // register compare; loads only on advance
                 ++mb;
@@ -401,10 +408,14 @@ score_refine_kernel(const float *__restrict__ Fu, const float *__restrict__ Fi,
                     const int32_t *__restrict__ cand_i, const float *__restrict__ tau,
                     int k, int32_t *__restrict__ out_ids,
                     float *__restrict__ out_scores, int32_t *__restrict__ fail) {
+    // blockIdx.y = item split: candidates, thresholds and the ordered top-k list of (split, user)
+    // live at index split*nu + user; with several splits the lists are merged (and certified) by
+    // merge_cert_kernel and `fail` is NULL here
     const int lane = threadIdx.x & 31;
-    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (q >= nu) return;
-    const float *fu = Fu + (size_t)users[q] * d;
+    const int64_t qu = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (qu >= nu) return;
+    const float *fu = Fu + (size_t)users[qu] * d;
+    const int64_t q = (int64_t)blockIdx.y * nu + qu;
     constexpr int CPL = CAND / 32;                 // candidates per lane
     float sc[CPL];
     int id[CPL];
@@ -452,7 +463,7 @@ score_refine_kernel(const float *__restrict__ Fu, const float *__restrict__ Fi,
         }
         kth = bs;
     }
-    if (lane == 0) {
+    if (lane == 0 && fail) {
         // every item the filter dropped has exact score <= key <= its group's threshold (the keys
         // are upper bounds of the exact scores): the k-th exact score must clear the largest one.
         float tq = tau[q * NB];
@@ -462,33 +473,112 @@ score_refine_kernel(const float *__restrict__ Fu, const float *__restrict__ Fi,
     }
 }
 
+// Item-split runs: merge the per-split ordered top-k lists of one user (exact scores, so the merge
+// is exact; (score desc, id asc) order) and certify against the largest threshold of ANY split /
+// epilogue group: every dropped item has exact <= key <= its own (split, group) threshold.
+__global__ void __launch_bounds__(256)
+merge_cert_kernel(const int32_t *__restrict__ p_ids, const float *__restrict__ p_sc,
+                  const float *__restrict__ tau, int64_t nu, int k, int n_splits,
+                  int32_t *__restrict__ out_ids, float *__restrict__ out_scores, int32_t *__restrict__ fail) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= nu) return;
+    constexpr int MAXL = 2;                       // n_splits <= 64: lane l walks lists l and l+32
+    int cur[MAXL] = {0, 0};
+    float kth = -FLT_MAX;
+    for (int r = 0; r < k; ++r) {
+        float bs = -FLT_MAX;
+        int bi = -1, bj = -1;
+#pragma unroll
+        for (int j = 0; j < MAXL; ++j) {
+            const int sp = lane + 32 * j;
+            if (sp < n_splits && cur[j] < k) {
+                const size_t o = ((size_t)sp * nu + q) * k + cur[j];
+                const float sc = p_sc[o];
+                const int id = p_ids[o];
+                if (id >= 0 && (bj < 0 || sc > bs || (sc == bs && id < bi))) { bs = sc; bi = id; bj = j; }
+            }
+        }
+        float ws = bs;
+        int wi = bi, wl = lane;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float os = __shfl_xor_sync(0xffffffffu, ws, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, wi, off);
+            const int ol = __shfl_xor_sync(0xffffffffu, wl, off);
+            if (oi >= 0 && (wi < 0 || os > ws || (os == ws && oi < wi))) { ws = os; wi = oi; wl = ol; }
+        }
+        if (lane == 0) { out_ids[q * k + r] = wi; out_scores[q * k + r] = wi >= 0 ? ws : -FLT_MAX; }
+        if (lane == wl && bj >= 0 && wi >= 0) {
+#pragma unroll
+            for (int j = 0; j < MAXL; ++j) if (j == bj) ++cur[j];
+        }
+        kth = wi >= 0 ? ws : -FLT_MAX;
+    }
+    float tq = -FLT_MAX;
+    for (int i = lane; i < n_splits * NB; i += 32) {
+        const int sp = i / NB, g = i % NB;
+        tq = fmaxf(tq, tau[((size_t)sp * nu + q) * NB + g]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) tq = fmaxf(tq, __shfl_xor_sync(0xffffffffu, tq, off));
+    if (lane == 0) fail[q] = (kth > tq) ? 0 : 1;
+}
+
 }  // namespace tc
 }  // namespace lgcn
 
 // ---- C ABI ---------------------------------------------------------------------------------
 namespace {
+// item splits so that a handful of user tiles (the reference rates 1024 users per batch,
+// main.py:415) still fills the chip: user_tiles * splits <= one wave of CTAs
+int tc_splits(int64_t nu, int64_t n_items) {
+    using namespace lgcn::tc;
+    const int64_t ut = (nu + MT - 1) / MT;
+    const int64_t n_tiles = (n_items + NT - 1) / NT;
+    if (ut <= 0 || ut >= lgcn::kNumSMs) return 1;
+    int64_t s = lgcn::kNumSMs / ut;
+    if (s > n_tiles / 32) s = n_tiles / 32;           // >= 32 tiles per split
+    if (s > 64) s = 64;
+    return s < 1 ? 1 : (int)s;
+}
+
 struct TcLayout {
-    size_t bt, vnorm, wnorm, cand_s, cand_i, tau, total;
+    size_t bt, vnorm, wnorm, cand_s, cand_i, tau, p_ids, p_sc, total;
+    int splits;
 };
 TcLayout tc_layout(int64_t nu, int64_t n_items, int32_t d) {
     using namespace lgcn::tc;
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     TcLayout L;
     const int64_t n_pad = (n_items + NT - 1) / NT * NT;
+    L.splits = tc_splits(nu, n_items);
+    const size_t rows = (size_t)nu * L.splits;          // (split, user) pairs
     L.bt = 0;                                           // prepared item tiles (independent of nu)
     L.vnorm = up(L.bt + (size_t)n_pad * d * 2);         // item norms (independent of nu)
     L.wnorm = up(L.vnorm + (size_t)n_pad * 4);          // largest norm per 32-item window
     L.cand_s = up(L.wnorm + (size_t)(n_pad / 32) * 4);
-    L.cand_i = up(L.cand_s + (size_t)nu * CAND * 4);
-    L.tau = up(L.cand_i + (size_t)nu * CAND * 4);
-    L.total = up(L.tau + (size_t)nu * 4 * lgcn::tc::NB);
+    L.cand_i = up(L.cand_s + rows * CAND * 4);
+    L.tau = up(L.cand_i + rows * CAND * 4);
+    L.p_ids = up(L.tau + rows * 4 * lgcn::tc::NB);      // per-split ordered top-k (splits > 1)
+    L.p_sc = up(L.p_ids + (L.splits > 1 ? rows * 32 * 4 : 0));
+    L.total = up(L.p_sc + (L.splits > 1 ? rows * 32 * 4 : 0));
     return L;
 }
 }  // namespace
 
+// The workspace serves every call with AT MOST nu users (a sweep reuses one workspace for all of
+// its batches, the last one shorter): fewer users mean more item splits, so take the largest.
 extern "C" size_t lgcn_score_tc_workspace(int64_t nu, int64_t n_items, int32_t d) {
     if (nu < 0 || n_items <= 0 || (d != 64 && d != 128)) return 0;
-    return tc_layout(nu, n_items, d).total;
+    size_t best = tc_layout(nu, n_items, d).total;
+    for (int64_t ut = 1; ut < lgcn::kNumSMs; ++ut) {
+        const int64_t n = ut * lgcn::tc::MT;
+        if (n >= nu) break;
+        const size_t t = tc_layout(n, n_items, d).total;
+        if (t > best) best = t;
+    }
+    return best;
 }
 
 extern "C" int lgcn_score_tc_prepare(const float *Fi, int64_t n_items, int32_t d, void *workspace,
@@ -537,27 +627,37 @@ extern "C" int lgcn_score_tc_topk(const float *Fu, const float *Fi, const int64_
     const float *vnorm = reinterpret_cast<const float *>(ws + L.vnorm);
     const float *wnorm = reinterpret_cast<const float *>(ws + L.wnorm);
     const int n_tiles = (int)((n_items + NT - 1) / NT);
-    const unsigned grid = (unsigned)((nu + MT - 1) / MT);
+    const int splits = L.splits;
+    const int tiles_per_split = (n_tiles + splits - 1) / splits;
+    const int splits_used = (n_tiles + tiles_per_split - 1) / tiles_per_split;
+    const dim3 grid((unsigned)((nu + MT - 1) / MT), (unsigned)splits_used);
     if (d == 64) {
-        static bool done = false;
-        if (!done) {
-            cudaError_t e = cudaFuncSetAttribute(score_filter_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FilterSmem<64>));
-            if (e != cudaSuccess) return (int)e;
-            done = true;
-        }
-        score_filter_kernel<64><<<grid, kThreads, sizeof(FilterSmem<64>), st>>>(Fu, users, nu, Bt, vnorm, wnorm, n_items, n_tiles, mask_rowptr, mask_col, cand_s, cand_i, tau);
+        LGCN_OPT_IN_SMEM((score_filter_kernel<64>), sizeof(FilterSmem<64>));
+        score_filter_kernel<64><<<grid, kThreads, sizeof(FilterSmem<64>), st>>>(Fu, users, nu, Bt, vnorm, wnorm, n_items, n_tiles, tiles_per_split, mask_rowptr, mask_col, cand_s, cand_i, tau);
     } else {
-        static bool done = false;
-        if (!done) {
-            cudaError_t e = cudaFuncSetAttribute(score_filter_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FilterSmem<128>));
-            if (e != cudaSuccess) return (int)e;
-            done = true;
-        }
-        score_filter_kernel<128><<<grid, kThreads, sizeof(FilterSmem<128>), st>>>(Fu, users, nu, Bt, vnorm, wnorm, n_items, n_tiles, mask_rowptr, mask_col, cand_s, cand_i, tau);
+        LGCN_OPT_IN_SMEM((score_filter_kernel<128>), sizeof(FilterSmem<128>));
+        score_filter_kernel<128><<<grid, kThreads, sizeof(FilterSmem<128>), st>>>(Fu, users, nu, Bt, vnorm, wnorm, n_items, n_tiles, tiles_per_split, mask_rowptr, mask_col, cand_s, cand_i, tau);
     }
     LGCN_LAUNCH_CHECK();
-    const unsigned rgrid = (unsigned)((nu * 32 + 255) / 256);
-    score_refine_kernel<<<rgrid, 256, 0, st>>>(Fu, Fi, users, nu, d, cand_i, tau, k, out_ids, out_scores, fail);
+    const dim3 rgrid((unsigned)((nu * 32 + 255) / 256), (unsigned)splits_used);
+    if (splits_used == 1) {
+        score_refine_kernel<<<rgrid, 256, 0, st>>>(Fu, Fi, users, nu, d, cand_i, tau, k, out_ids, out_scores, fail);
+        LGCN_LAUNCH_CHECK();
+        return 0;
+    }
+    int32_t *p_ids = reinterpret_cast<int32_t *>(ws + L.p_ids);
+    float *p_sc = reinterpret_cast<float *>(ws + L.p_sc);
+    score_refine_kernel<<<rgrid, 256, 0, st>>>(Fu, Fi, users, nu, d, cand_i, tau, k, p_ids, p_sc, nullptr);
+    LGCN_LAUNCH_CHECK();
+    merge_cert_kernel<<<(unsigned)((nu * 32 + 255) / 256), 256, 0, st>>>(p_ids, p_sc, tau, nu, k, splits_used,
+                                                                           out_ids, out_scores, fail);
     LGCN_LAUNCH_CHECK();
     return 0;
+}
+
+// Host-only query: kernels one lgcn_score_tc_topk call launches (2 = filter + refine, 3 with the
+// merge of an item-split run) -- for launch accounting.
+extern "C" int lgcn_score_tc_launches(int64_t nu, int64_t n_items) {
+    if (nu <= 0 || n_items <= 0) return 0;
+    return tc_splits(nu, n_items) > 1 ? 3 : 2;
 }

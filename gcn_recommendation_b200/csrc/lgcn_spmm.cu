@@ -18,6 +18,7 @@
 // Finished rows are staged in shared memory; the epilogue then streams the chunk's R rows with
 // all of its operand loads independent (mean of the earlier layers / Horner addend / Adam).
 #include <limits.h>
+#include <stdio.h>
 
 #include <type_traits>
 
@@ -912,13 +913,7 @@ __global__ void __launch_bounds__(kThreads) spmm_long_combine_kernel(const __gri
 template <int D, int MODE, int RSEL, bool HINT, bool XF>
 static int launch_chunks(const lgcn_spmm_args &a, cudaStream_t st) {
     using C = ChunkCfg<D, RSEL>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(spmm_chunk_kernel<D, MODE, RSEL, HINT, XF>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        if (e != cudaSuccess) return (int)e;
-        attr_done = true;
-    }
+    LGCN_OPT_IN_SMEM((spmm_chunk_kernel<D, MODE, RSEL, HINT, XF>), C::SMEM);
     int64_t gb = (a.n_rows + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
     if (RSEL == 1 && a.n_long > 0)          // + the long-row segment workers (see the kernel)
         gb += (a.n_seg + kWarps * RowGeom<D>::GROUPS - 1) / (kWarps * RowGeom<D>::GROUPS);
@@ -931,13 +926,7 @@ static int launch_chunks(const lgcn_spmm_args &a, cudaStream_t st) {
 template <int D, bool HINT>
 static int launch_live(const lgcn_spmm_args &a, cudaStream_t st) {
     using C = RingCfg<D>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(spmm_live_kernel<D, HINT>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        if (e != cudaSuccess) return (int)e;
-        attr_done = true;
-    }
+    LGCN_OPT_IN_SMEM((spmm_live_kernel<D, HINT>), C::SMEM);
     const int64_t gb = (a.n_rows + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
     if (gb > 0x7fffffffLL) return LGCN_E_TOO_LARGE;
     spmm_live_kernel<D, HINT><<<(unsigned)gb, kRingWarps * 32, C::SMEM, st>>>(a);
@@ -948,13 +937,7 @@ static int launch_live(const lgcn_spmm_args &a, cudaStream_t st) {
 template <int D, int MODE, bool HINT>
 static int launch_ring(const lgcn_spmm_args &a, cudaStream_t st) {
     using C = RingCfg<D>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(spmm_ring_kernel<D, MODE, HINT>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        if (e != cudaSuccess) return (int)e;
-        attr_done = true;
-    }
+    LGCN_OPT_IN_SMEM((spmm_ring_kernel<D, MODE, HINT>), C::SMEM);
     const int64_t gb = (a.n_rows + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
     if (gb > 0x7fffffffLL) return LGCN_E_TOO_LARGE;
     spmm_ring_kernel<D, MODE, HINT><<<(unsigned)gb, kRingWarps * 32, C::SMEM, st>>>(a);
@@ -968,6 +951,13 @@ template <int D>
 static bool small_graph(int64_t n_rows, int32_t flags) {
     const int64_t big_workers = n_rows / ChunkCfg<D, 0>::R;
     return big_workers < (int64_t)kNumSMs * 32 * RowGeom<D>::GROUPS && !(flags & LGCN_SPMM_F_BIG_PATH);
+}
+
+// Large graphs: the cp.async ring kernel; the flagged (sparse-input) hops run the live-list
+// kernel.  ADAM (its epilogue wants the registers) keeps the register-batch chunk kernel.
+static bool ring_path(bool small, int mode, int32_t flags) {
+    return !small && !(flags & LGCN_SPMM_F_NO_RING) &&
+           (mode != LGCN_SPMM_ADAM || (flags & LGCN_SPMM_F_FORCE_RING));
 }
 
 template <int D, int MODE>
@@ -984,10 +974,7 @@ static int launch_mode(const lgcn_spmm_args &a, cudaStream_t st) {
         const bool hint = (a.flags & LGCN_SPMM_F_STREAM_HINTS) != 0;
         int rc;
         const bool xf = MODE == LGCN_SPMM_ADD && a.x_rowflag != nullptr;
-        // Large graphs: the cp.async ring kernel; the flagged (sparse-input) hops run the live-list
-        // kernel.  ADAM (its epilogue wants the registers) keeps the register-batch chunk kernel.
-        const bool ring = !small && !(a.flags & LGCN_SPMM_F_NO_RING) &&
-                          (MODE != LGCN_SPMM_ADAM || (a.flags & LGCN_SPMM_F_FORCE_RING));
+        const bool ring = ring_path(small, MODE, a.flags);
         if (ring && xf) {
             rc = hint ? launch_live<D, true>(a, st) : launch_live<D, false>(a, st);
         } else if (ring) {
@@ -1062,19 +1049,43 @@ extern "C" int lgcn_spmm(const lgcn_spmm_args *args, lgcn_stream_t stream) {
 
 extern "C" size_t lgcn_sizeof_spmm_args(void) { return sizeof(lgcn_spmm_args); }
 
+static bool small_for_dim(int64_t n_rows, int32_t d, int32_t flags) {
+    using namespace lgcn;
+    switch (d) {
+        case 16:  return small_graph<16>(n_rows, flags);
+        case 32:  return small_graph<32>(n_rows, flags);
+        case 64:  return small_graph<64>(n_rows, flags);
+        case 128: return small_graph<128>(n_rows, flags);
+        case 256: return small_graph<256>(n_rows, flags);
+    }
+    return false;
+}
+
+extern "C" int lgcn_spmm_kernel_name(int64_t n_rows, int32_t d, int32_t mode, int32_t flags,
+                                     int32_t sparse_x, char *buf, size_t buf_bytes) {
+    using namespace lgcn;
+    if (!dim_supported(d)) return LGCN_E_BAD_DIM;
+    if (n_rows < 0 || !buf || buf_bytes == 0 || mode < LGCN_SPMM_PLAIN || mode > LGCN_SPMM_ADAM)
+        return LGCN_E_BAD_ARG;
+    static const char *const kMode[] = {"plain", "add", "mean", "adam"};
+    const bool small = small_for_dim(n_rows, d, flags);
+    const bool hint = (flags & LGCN_SPMM_F_STREAM_HINTS) != 0;
+    const bool xf = mode == LGCN_SPMM_ADD && sparse_x != 0;
+    const bool ring = ring_path(small, mode, flags);
+    if (ring && xf) snprintf(buf, buf_bytes, "spmm_live_kernel<%d,%s>", d, hint ? "hints" : "nohints");
+    else if (ring) snprintf(buf, buf_bytes, "spmm_ring_kernel<%d,%s,%s>", d, kMode[mode], hint ? "hints" : "nohints");
+    else snprintf(buf, buf_bytes, "spmm_chunk_kernel<%d,%s,%s,%s%s>", d, kMode[mode],
+                  small ? "4-row chunks" : "16-row chunks", (hint && !small) ? "hints" : "nohints",
+                  xf ? ",sparse-x" : "");
+    return 0;
+}
+
 extern "C" int lgcn_spmm_launches(int64_t n_rows, int32_t d, int32_t n_long, int32_t flags,
                                   int32_t *small_path) {
     using namespace lgcn;
     if (!dim_supported(d)) return LGCN_E_BAD_DIM;
     if (n_rows < 0 || n_long < 0) return LGCN_E_BAD_ARG;
-    bool small = false;
-    switch (d) {
-        case 16:  small = small_graph<16>(n_rows, flags); break;
-        case 32:  small = small_graph<32>(n_rows, flags); break;
-        case 64:  small = small_graph<64>(n_rows, flags); break;
-        case 128: small = small_graph<128>(n_rows, flags); break;
-        case 256: small = small_graph<256>(n_rows, flags); break;
-    }
+    const bool small = small_for_dim(n_rows, d, flags);
     if (small_path) *small_path = small ? 1 : 0;
     if (n_long == 0) return 1;                 // main kernel only
     return small ? 2 : 3;                      // (+ segments) + combine

@@ -68,6 +68,9 @@ class FeatureShardedEngine(LightGCNEngine):
         super()._alloc_batch(bs)
         self.dots = torch.empty(3 * bs, dtype=torch.float32, device=self.dev)
 
+    def _extra_batch_buffers(self):
+        return ("dots",)
+
     # ---- LightGCN_Fusion item block (reference models/lightgcn_fusion.py:45-49) -------------
     # The projection mixes ALL d features of an item row, so it cannot run on column shards.
     # It is sharded by ITEM instead: rank r owns the content rows of item block
@@ -172,14 +175,16 @@ class FeatureShardedEngine(LightGCNEngine):
         F = self.propagate()
         return self._gather_columns(F)
 
-    def evaluate(self, eval_users, targets, mask_rowptr, mask_col, k=20, propagate=True):
+    def evaluate(self, eval_users, targets, mask_rowptr, mask_col, k=20, propagate=True, batch_users=None):
         """User-sharded full-rank evaluation (reference ``main.py:404-439``): the caller passes
         THIS rank's users / targets / mask rows; hit and DCG sums are all-reduced."""
         if propagate or getattr(self, "_F_full", None) is None:
+            self._F_full = None                     # release the old gathered table first
             self._F_full = self.gather_final_table()
+            if self._tc is not None:
+                self._tc.prepared_for = None
         F = self._F_full
-        ids, _ = ops.score_topk(F[:self.U], F[self.U:self.U + self.I], eval_users, mask_rowptr,
-                                mask_col, k)
+        ids, _ = self._rate(F, eval_users, mask_rowptr, mask_col, k, batch_users)
         sums = torch.zeros(3, dtype=torch.float64, device=self.dev)
         ops.eval_metrics(ids, targets, sums[:2])
         sums[2] = eval_users.numel()
@@ -231,6 +236,8 @@ class RowShardedEngine:
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self.bs = int(batch_size)
         self.sample_ws = torch.empty(2 * self.bs, dtype=torch.float32, device=self.dev)
+        self.idx_status = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._checked_bs = -1
         self.Gfull = torch.zeros((self.rpr * P_, self.d), dtype=torch.float32, device=self.dev)
         self.G2full = torch.zeros((self.rpr * P_, self.d), dtype=torch.float32, device=self.dev)
         per_spmm = ops.spmm_launches(self.g, self.d) if self.g is not None else 1
@@ -255,7 +262,20 @@ class RowShardedEngine:
     def bpr_step(self, users, pos, neg, use_graph=False):
         K, U = self.K, self.U
         dev = self.dev
+        bs = users.numel()
+        if not (pos.numel() == bs and neg.numel() == bs):
+            raise LgcnError("users, pos and neg must have the same length")
+        if bs != self.bs:                          # the fused BPR kernel writes sample_ws[0 : 2*bs]
+            self.bs = bs
+            self.sample_ws = torch.empty(2 * bs, dtype=torch.float32, device=dev)
+            self._checked_bs = -1
         u, p, n = users.to(dev, non_blocking=True), pos.to(dev, non_blocking=True), neg.to(dev, non_blocking=True)
+        if self._checked_bs != bs:
+            self.idx_status.zero_()
+            ops.check_indices(self.idx_status, (u, 0, self.U), (p, 0, self.I), (n, 0, self.I))
+            if int(self.idx_status.item()) != 0:
+                raise IndexError("batch indices are out of range")
+            self._checked_bs = bs
         self.propagate()
         F_full = self._gather(self.Floc, self.Xa if (K - 1) % 2 == 0 else self.Xb)
         # every rank forms the whole batch redundantly; gradients land in full-size scratch
@@ -274,3 +294,40 @@ class RowShardedEngine:
                       betas=self.betas, eps=self.eps)
         ops.zero_rows(self.Gfull, self.G2full, u, p, n, U)
         return self.loss
+
+    # ---- reference-format checkpoints and evaluation from row blocks ----------------------------
+    fusion = None
+
+    def _full_table(self):
+        """All-gather the parameter row blocks -> [N, d] on every rank."""
+        return self._gather(self.P, self.P_full)[:self.N]
+
+    def _local_columns(self, full):
+        """The padded row block of this rank out of a full [N, d] table (name kept from the
+        feature-sharded engine: it is what ``load_state_dict`` copies into ``P``)."""
+        blk = torch.zeros((self.rpr, self.d), dtype=torch.float32, device=self.dev)
+        if self.nloc > 0:
+            blk[:self.nloc].copy_(full[self.r0:self.r1])
+        return blk
+
+    state_dict = LightGCNEngine.state_dict
+    load_state_dict = LightGCNEngine.load_state_dict
+
+    def gather_final_table(self):
+        self.propagate()
+        return self._gather(self.Floc, self.Xa)[:self.N]
+
+    def evaluate(self, eval_users, targets, mask_rowptr, mask_col, k=20, propagate=True, batch_users=None):
+        """User-sharded full-rank evaluation (reference ``main.py:404-439``): this rank's users /
+        targets / mask rows against the all-gathered final table; sums all-reduced."""
+        if propagate or getattr(self, "_F_full", None) is None:
+            self._F_full = self.gather_final_table()
+        F = self._F_full
+        ids, _ = ops.score_topk(F[:self.U], F[self.U:self.U + self.I], eval_users, mask_rowptr,
+                                mask_col, k, batch_users=batch_users)
+        sums = torch.zeros(3, dtype=torch.float64, device=self.dev)
+        ops.eval_metrics(ids, targets, sums[:2])
+        sums[2] = eval_users.numel()
+        dist.all_reduce(sums, group=self.group)
+        s = sums.cpu().numpy()
+        return float(s[0] / s[2]), float(s[1] / s[2]), ids

@@ -23,6 +23,8 @@ import torch
 from . import ops
 from ._lib import LgcnError
 
+_CHECK_ALWAYS = os.environ.get("LGCN_CHECK_INDICES", "0") == "1"
+
 
 def build_mask_csr(eval_users, train_user, train_item, num_users, device=None):
     """Per-evaluated-user ascending train-item lists as CSR over the position in ``eval_users``
@@ -85,7 +87,9 @@ class LightGCNEngine:
         self.m = torch.zeros_like(self.P)
         self.v = torch.zeros_like(self.P)
         self.F = new()
-        self.work = [new() for _ in range(max(self.K - 1, 2 if self.K > 1 else 0))]
+        # E_1..E_{K-1}, reused as the Horner ping-pong; K == 1 with the fusion block still runs one
+        # backward hop, which must not land in F (rate_topk(propagate=False) reads F afterwards)
+        self.work = [new() for _ in range(max(self.K - 1, 2 if self.K > 1 else (1 if fusion is not None else 0)))]
         self.G1 = torch.zeros_like(self.P)          # g/(K+1): addend of every Horner hop
         self.G2 = torch.zeros_like(self.P)          # regulariser grad (+ g/(K+1) w/o fusion)
         # 1 = row received a gradient this step (G1/G2 are zero elsewhere): lets the backward
@@ -98,6 +102,7 @@ class LightGCNEngine:
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.adam_scalars = torch.zeros(2, dtype=torch.float32, device=self.dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.idx_status = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.bs = int(batch_size)
         # Sparse first-hop output + flagged second hop: pays when the tables stream from HBM
         # (Amazon shape: 4.6 + 5.2 -> 1.8 + 3.5 ms); on L2-resident graphs the extra flag lookups
@@ -110,11 +115,14 @@ class LightGCNEngine:
         if fusion is not None:
             self._init_fusion(fusion)
         self._graph = None
+        self._tc = None                             # ops.TcRater of the evaluation sweep
+        self._idx_checked_eval = None
         self.launches_per_step = self._count_launches()
 
     # ---- setup ---------------------------------------------------------------------------
     def _alloc_batch(self, bs):
         self.bs = bs
+        self._checked_bs = -1
         self.b_users = torch.zeros(bs, dtype=torch.int64, device=self.dev)
         self.b_pos = torch.zeros(bs, dtype=torch.int64, device=self.dev)
         self.b_neg = torch.zeros(bs, dtype=torch.int64, device=self.dev)
@@ -163,6 +171,8 @@ class LightGCNEngine:
 
     def propagate(self):
         """F = mean_k A^k E0 (reference ``models/lightgcn.py:44-54``); returns the [N,d] table."""
+        if self._tc is not None:
+            self._tc.prepared_for = None            # the bf16 item tiles belong to the old table
         return ops.propagate(self.g, self.layer0(), self.K, out=self.F, work=self.work)
 
     def forward(self):
@@ -195,7 +205,7 @@ class LightGCNEngine:
             # rows next to the batch's nodes are written (flags in rf2); hop 1 gathers under rf2
             # (still ~80 % zero rows at the Amazon shape).  The addend of every hop is g' too: its
             # all-zero rows are not read (1 ms per hop at the Amazon shape)
-            acc = ops.spmm(g, acc, out=self.work[k % 2] if K > 1 else self.F, addend=self.G1,
+            acc = ops.spmm(g, acc, out=self.work[k % 2] if K > 1 else self.work[0], addend=self.G1,
                            x_rowflag=rf if k == 0 else (rf2 if k == 1 else None), addend_rowflag=rf,
                            zero_row=zr, y_rowflag=rf2 if k == 0 else None)
         if nofus:
@@ -248,16 +258,35 @@ class LightGCNEngine:
             for k, t in zip(("W", "b", "mW", "vW", "mb", "vb"), st[4:]):
                 f[k].copy_(t)
 
+    def _check_batch(self, users, pos, neg):
+        """Range check of a batch (the reference's gathers raise IndexError, main.py:496-497).
+        Costs a device->host read, so it runs for the first batch of every new batch size and on
+        every batch with LGCN_CHECK_INDICES=1."""
+        self.idx_status.zero_()
+        ops.check_indices(self.idx_status, (users, 0, self.U), (pos, 0, self.I), (neg, 0, self.I))
+        if int(self.idx_status.item()) != 0:
+            raise IndexError(f"{int(self.idx_status.item())} batch indices are out of range "
+                             f"(users < {self.U}, items < {self.I})")
+
     def bpr_step(self, users, pos, neg, use_graph=True):
         """One fused training step on a (users, pos, neg) int64 batch (host or device tensors).
         Returns the device loss tensor [1] (read it with ``.item()`` only when needed; reference
         ``main.py:528`` syncs every step)."""
         bs = users.numel()
-        if bs != self.bs:
+        if not (pos.numel() == bs and neg.numel() == bs):
+            raise LgcnError("users, pos and neg must have the same length")
+        if bs > self.bs or (bs < self.bs and self._graph is None) or bs == 0:
             self._alloc_batch(bs)
+        if bs < self.bs:
+            # a shorter (tail) batch while a step is captured for the full size: run it eagerly on
+            # views of the staging buffers, the captured graph stays valid
+            return self._tail_step(users, pos, neg, bs)
         self.b_users.copy_(users, non_blocking=True)
         self.b_pos.copy_(pos, non_blocking=True)
         self.b_neg.copy_(neg, non_blocking=True)
+        if self._checked_bs != bs or _CHECK_ALWAYS:
+            self._check_batch(self.b_users, self.b_pos, self.b_neg)
+            self._checked_bs = bs
         if use_graph:
             if self._graph is None:
                 self.capture()
@@ -266,10 +295,36 @@ class LightGCNEngine:
             self._step_body()
         return self.loss
 
+    _BATCH_BUFFERS = ("b_users", "b_pos", "b_neg")
+
+    def _tail_step(self, users, pos, neg, bs):
+        full = {k: getattr(self, k) for k in self._BATCH_BUFFERS + ("sample_ws",) + self._extra_batch_buffers()}
+        try:
+            for k, t in full.items():
+                per = t.numel() // self.bs
+                setattr(self, k, t[:bs * per])
+            self.b_users.copy_(users, non_blocking=True)
+            self.b_pos.copy_(pos, non_blocking=True)
+            self.b_neg.copy_(neg, non_blocking=True)
+            self._check_batch(self.b_users, self.b_pos, self.b_neg)
+            self._step_body()
+        finally:
+            for k, t in full.items():
+                setattr(self, k, t)
+        return self.loss
+
+    def _extra_batch_buffers(self):
+        return ()
+
     def train_steps(self, n_steps, seed=42, use_graph=False):
         """``n_steps`` training steps on batches drawn by the device-side sampler (replaces the
         reference's DataLoader, ``main.py:462-464,488``): nothing crosses the PCIe bus.  Returns
-        the device loss of the last step."""
+        the device loss of the last step.
+
+        An epoch visits every UNIQUE (user, item) training pair once (``rowptr[U]`` entries of the
+        CSR); the reference's DataLoader visits ``len(train_df)`` rows, i.e. a repeated interaction
+        as many times as it occurs in train.parquet (``main.py:349-363``).  The two agree on
+        deduplicated data, which is what the reference's prepare_data scripts write."""
         if not hasattr(self, "sampler_state"):
             self.sampler_state = torch.zeros(2, dtype=torch.int64, device=self.dev)
             self.n_edges = int(self.g.rowptr[self.U].item())
@@ -336,19 +391,40 @@ class LightGCNEngine:
         F = self.propagate()
         return ops.bpr_fused(F, self.P, users, pos, neg, self.U, self.lam)
 
-    def rate_topk(self, users, mask_rowptr=None, mask_col=None, k=20, propagate=True):
-        """Full-rank top-k item ids for ``users`` with their train items excluded (reference
-        ``main.py:413-426``)."""
-        F = self.propagate() if propagate else self.F
-        return ops.score_topk(F[:self.U], F[self.U:self.U + self.I], users, mask_rowptr, mask_col, k)
+    def _rate(self, F, users, mask_rowptr, mask_col, k, batch_users=None):
+        """Batched full-rank rating against the [N, d] table ``F`` with a rater (prepared bf16 item
+        tiles + workspace) that lives across calls; ``propagate`` invalidates the prepared tiles."""
+        if (users.numel() and (self._idx_checked_eval is not users)) or _CHECK_ALWAYS:
+            self.idx_status.zero_()
+            ops.check_indices(self.idx_status, (users, 0, self.U))
+            if int(self.idx_status.item()) != 0:
+                raise IndexError("evaluation user index out of range")
+            self._idx_checked_eval = users
+        Fu, Fi = F[:self.U], F[self.U:self.U + self.I]
+        d = F.shape[1]
+        rater = None
+        if d in (64, 128) and self.I >= ops.TC_MIN_ITEMS and k <= 32 and users.numel() > 0:
+            want = min(users.numel(), batch_users or ops.TC_WAVE_USERS * ops.TC_BATCH_WAVES)
+            if self._tc is None or self._tc.max_users < want or self._tc.d != d:
+                self._tc = ops.TcRater(self.I, d, self.dev, want)
+            rater = self._tc
+        return ops.score_topk(Fu, Fi, users, mask_rowptr, mask_col, k, rater=rater,
+                              batch_users=batch_users)
 
-    def evaluate(self, eval_users, targets, mask_rowptr, mask_col, k=20, propagate=True):
+    def rate_topk(self, users, mask_rowptr=None, mask_col=None, k=20, propagate=True, batch_users=None):
+        """Full-rank top-k item ids for ``users`` with their train items excluded (reference
+        ``main.py:413-426``); any number of users -- the sweep runs in user batches."""
+        F = self.propagate() if propagate else self.F
+        return self._rate(F, users, mask_rowptr, mask_col, k, batch_users)
+
+    def evaluate(self, eval_users, targets, mask_rowptr, mask_col, k=20, propagate=True, batch_users=None):
         """recall@k / NDCG@k as reference ``main.py:404-439``.  Returns (recall, ndcg, ids)."""
         if propagate:
             self.propagate()
         nu = eval_users.numel()
         sums = torch.zeros(2, dtype=torch.float64, device=self.dev)
-        ids, _ = self.rate_topk(eval_users, mask_rowptr, mask_col, k, propagate=False)
+        ids, _ = self.rate_topk(eval_users, mask_rowptr, mask_col, k, propagate=False,
+                                batch_users=batch_users)
         ops.eval_metrics(ids, targets, sums)
         s = sums.cpu().numpy()
         return float(s[0] / nu), float(s[1] / nu), ids

@@ -37,6 +37,9 @@ class NormAdjCSR:
         self.nnz = int(col.numel())
         self.device = rowptr.device
         self._seg_ws = {}
+        # True: A == A^T was verified; None: built by from_interactions (symmetric by
+        # construction, reference main.py:304-313); False: backward through this CSR is refused
+        self.symmetric = None
         if long_row_threshold is None and os.environ.get("LGCN_LONG_ROW_THRESHOLD"):
             long_row_threshold = int(os.environ["LGCN_LONG_ROW_THRESHOLD"])      # tuning hook
             seg_len = int(os.environ.get("LGCN_SEG_LEN", max(long_row_threshold // 2, 8)))
@@ -264,12 +267,15 @@ class NormAdjCSR:
             rowptr = torch.empty(N + 1, dtype=torch.int32, device=adj_mat.device)
             col = torch.empty(nnz, dtype=torch.int32, device=adj_mat.device)
             status = torch.zeros(1, dtype=torch.int32, device=adj_mat.device)
-            _lib.check(lib.lgcn_csr_from_sorted_coo(_lib.ptr(row, "i64"), _lib.ptr(colin, "i64"), nnz,
-                                                    N, _lib.ptr(rowptr, "i32"), _lib.ptr(col, "i32"),
-                                                    _lib.ptr(status, "i32"),
-                                                    _lib.stream_ptr(adj_mat.device)))
+            with torch.cuda.device(adj_mat.device):
+                _lib.check(lib.lgcn_csr_from_sorted_coo(_lib.ptr(row, "i64"), _lib.ptr(colin, "i64"), nnz,
+                                                        N, int(adj_mat.shape[1]), _lib.ptr(rowptr, "i32"),
+                                                        _lib.ptr(col, "i32"), _lib.ptr(status, "i32"),
+                                                        _lib.stream_ptr(adj_mat.device)))
             if int(status.item()) == 0:
-                return cls(rowptr, col, vals.contiguous().clone(), adj_mat.shape[1], **kw)
+                g = cls(rowptr, col, vals.contiguous().clone(), adj_mat.shape[1], **kw)
+                g.symmetric = _is_symmetric(row, colin, g.val, N, adj_mat.shape[1])
+                return g
             if attempt == 0:
                 adj_mat = adj_mat.coalesce()
         raise _lib.LgcnError("adjacency indices are out of range")
@@ -284,6 +290,19 @@ class NormAdjCSR:
         if self.n_rows == self.n_cols:
             g.col_degree = self.rowptr[1:] - self.rowptr[:-1]
         return g
+
+
+def _is_symmetric(row, col, val, n_rows, n_cols):
+    """A == A^T for a strictly (row, col)-sorted COO: the transposed keys, sorted, must be the same
+    key list with the same values.  Device integer work, once per adjacency (the backward pass
+    reuses the forward CSR, which is only valid for a symmetric matrix)."""
+    if n_rows != n_cols:
+        return False
+    key_t, order = torch.sort(col * n_rows + row)
+    if not torch.equal(key_t, row * n_rows + col):
+        return False
+    # D^-1/2 A D^-1/2 rounds (d_r*m)*d_c and (d_c*m)*d_r separately: up to 1 ulp apart
+    return bool(torch.allclose(val[order], val, rtol=1e-6, atol=0.0))
 
 
 _COO_CACHE = {}

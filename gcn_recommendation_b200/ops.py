@@ -6,6 +6,7 @@ Everything here launches hand-written sm_100a kernels; there is no eager/PyTorch
 from __future__ import annotations
 
 import ctypes
+import functools
 import os
 
 import torch
@@ -26,6 +27,30 @@ PROFILE = None
 # L2 does not retain the hot rows under 6 TB/s of streaming (sector hit rate 11.5 -> 12.9 %).
 HOT_BYTES = int(float(os.environ.get("LGCN_HOT_MB", "32")) * (1 << 20))
 SPMM_FLAGS_EXTRA = int(os.environ.get("LGCN_SPMM_FLAGS", "0"))           # OR-ed into lgcn_spmm_args.flags (tests / A-B measurements force a kernel)
+
+
+def _device_of(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return a.device
+        elif hasattr(a, "rowptr_flagged"):            # graph.NormAdjCSR
+            return a.device
+    return None
+
+
+def on_device(fn):
+    """Run an operator with the CUDA device of its first tensor / graph argument current: the
+    library launches on the current context (cudaFuncSetAttribute, <<<>>>), so a tensor on cuda:1
+    while cuda:0 is current must switch first.  One integer compare when they already agree."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = _device_of(args, kwargs)
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
 
 
 def _spmm_plan(n_rows, d, n_long):
@@ -84,14 +109,17 @@ def _spmm_args(g, x, mode, d):
     return a
 
 
-def spmm_kernel_name(g, d, mode):
-    """Name of the kernel ``lgcn_spmm`` picks for this graph / width / mode (mirrors the selection
-    in csrc/lgcn_spmm.cu ``launch_mode``; used by bench.py to label the roofline)."""
-    if _small_graph(g.n_rows, d):
-        return f"spmm_chunk_kernel<{d},{mode},4-row chunks>"
-    if mode == "adam":
-        return f"spmm_chunk_kernel<{d},{mode}>"
-    return f"spmm_ring_kernel<{d},{mode}>"
+def spmm_kernel_name(g, d, mode, sparse_x=False):
+    """Name of the main kernel ``lgcn_spmm`` picks for this graph / width / mode (host-only query
+    of the library's own selection, csrc/lgcn_spmm.cu ``launch_mode``; bench.py labels the
+    roofline with it)."""
+    code = {"plain": SPMM_PLAIN, "add": SPMM_ADD, "add_xs": SPMM_ADD, "add_xf": SPMM_ADD,
+            "mean": SPMM_MEAN, "adam": SPMM_ADAM}[mode]
+    flags = SPMM_FLAGS_EXTRA | (_lib.SPMM_F_STREAM_HINTS if g.n_cols * d * 4 > L2_STREAM_BYTES else 0)
+    buf = ctypes.create_string_buffer(128)
+    check(_lib.load().lgcn_spmm_kernel_name(int(g.n_rows), int(d), code, flags,
+                                            int(sparse_x or mode in ("add_xs", "add_xf")), buf, 128))
+    return buf.value.decode()
 
 
 def _check_table(t, rows, d, name):
@@ -99,6 +127,7 @@ def _check_table(t, rows, d, name):
         raise _lib.LgcnError(f"{name}: expected at least [{rows},{d}], got {tuple(t.shape)}")
 
 
+@on_device
 def spmm(g, x, out=None, addend=None, mean_layers=None, x_rowflag=None, addend_rowflag=None,
          zero_row=None, y_rowflag=None):
     """out = A_hat x  (+ addend)  |  mean over [*mean_layers, A_hat x] (reference
@@ -145,6 +174,7 @@ def spmm(g, x, out=None, addend=None, mean_layers=None, x_rowflag=None, addend_r
     return out
 
 
+@on_device
 def spmm_adam(g, x, p, m, v, adam_scalars, addend=None, addend2=None, betas=(0.9, 0.999),
               eps=1e-8, g_out=None, addend_rowflag=None, zero_row=None):
     """Last backward hop fused with Adam: grad = addend + A_hat x + addend2; Adam(p, m, v, grad)
@@ -189,6 +219,7 @@ def propagate_backward(g, grad_f, n_layers, work=None):
     return acc
 
 
+@on_device
 def bpr_fused(F, P, users, pos, neg, num_users, lam, grad_scale=1.0, gF=None, gP=None,
               gp_includes_gf=False, sample_ws=None, loss_out=None, rowflag=None):
     """Fused gather + BPR + L2 + scatter-add (reference ``main.py:366-402,496-497``)."""
@@ -213,6 +244,7 @@ def bpr_fused(F, P, users, pos, neg, num_users, lam, grad_scale=1.0, gF=None, gP
     return loss_out
 
 
+@on_device
 def bpr_partial(F, P, users, pos, neg, num_users, dots):
     """Feature-sharded step, phase 1: this rank's partial <u,p>, <u,n>, |.|^2 per sample."""
     COUNTERS["launches"] += 1
@@ -222,6 +254,7 @@ def bpr_partial(F, P, users, pos, neg, num_users, dots):
     return dots
 
 
+@on_device
 def bpr_apply(F, P, users, pos, neg, num_users, lam, dots, grad_scale=1.0, gF=None, gP=None,
               gp_includes_gf=False, sample_ws=None, loss_out=None, rowflag=None):
     """Feature-sharded step, phase 2: loss from the rank-summed dots, scatter local columns."""
@@ -245,6 +278,7 @@ def bpr_apply(F, P, users, pos, neg, num_users, lam, dots, grad_scale=1.0, gF=No
     return loss_out
 
 
+@on_device
 def zero_rows(t0, t1, users, pos, neg, num_users, rowflag=None):
     d = t0.shape[1]
     COUNTERS["launches"] += 1
@@ -254,6 +288,7 @@ def zero_rows(t0, t1, users, pos, neg, num_users, rowflag=None):
                                      stream_ptr(t0.device)))
 
 
+@on_device
 def sample_bpr(g, num_users, num_items, n_edges, seed, state, users, pos, neg):
     """Next batch of (user, pos, neg) triplets on the device (reference ``main.py:349-363``):
     one epoch = a keyed random permutation of the training interactions, negatives uniform over
@@ -265,12 +300,27 @@ def sample_bpr(g, num_users, num_items, n_edges, seed, state, users, pos, neg):
                                       stream_ptr(users.device)))
 
 
+@on_device
+def check_indices(status, *ranges):
+    """status[0] += how many indices fall outside their range; ``ranges`` = (idx int64 tensor, lo,
+    hi) triples.  The reference's gathers raise IndexError for those (main.py:496-497); here the
+    caller reads ``status`` when it wants the verdict (no sync on the step path)."""
+    lib = _lib.load()
+    for idx, lo, hi in ranges:
+        COUNTERS["launches"] += 1
+        check(lib.lgcn_check_indices(ptr(idx, "i64"), idx.numel(), int(lo), int(hi),
+                                     ptr(status, "i32"), stream_ptr(idx.device)))
+    return status
+
+
+@on_device
 def adam_tick(step_dev, scalars, lr, betas=(0.9, 0.999)):
     COUNTERS["launches"] += 1
     check(_lib.load().lgcn_adam_tick(ptr(step_dev, "i64"), ptr(scalars), lr, betas[0], betas[1],
                                      stream_ptr(scalars.device)))
 
 
+@on_device
 def adam(p, g0, m, v, scalars, g1=None, betas=(0.9, 0.999), eps=1e-8):
     COUNTERS["launches"] += 1
     check(_lib.load().lgcn_adam(ptr(p), ptr(g0), ptr(g1, allow_none=True), ptr(m), ptr(v),
@@ -278,6 +328,7 @@ def adam(p, g0, m, v, scalars, g1=None, betas=(0.9, 0.999), eps=1e-8):
                                 stream_ptr(p.device)))
 
 
+@on_device
 def fusion_proj_fwd(e_id, content, W, b, out=None):
     """leaky_relu([E_id | C] W^T + b) without the concat (reference
     ``models/lightgcn_fusion.py:45-49``)."""
@@ -293,6 +344,7 @@ def fusion_proj_fwd(e_id, content, W, b, out=None):
     return out
 
 
+@on_device
 def fusion_proj_bwd(e_id, content, W, H, gH, g_eid=None, gW=None, gb=None):
     n, d = e_id.shape
     c = content.shape[1]
@@ -313,6 +365,7 @@ TC_MIN_ITEMS = 8192       # below this the exact SIMT kernel is used directly
 STATS = {"tc_users": 0, "tc_fallback_users": 0}
 
 
+@on_device
 def score_topk_exact(F_user, F_item, users, mask_rowptr=None, mask_col=None, k=20):
     """Exact fp32 SIMT kernel (sequential FMA scores): the reference's arithmetic."""
     nu = users.numel()
@@ -343,11 +396,60 @@ def _sub_csr(rowptr, col, idx):
     return rp, col[src].contiguous()
 
 
-def score_topk(F_user, F_item, users, mask_rowptr=None, mask_col=None, k=20, tensor_cores=None):
+class TcRater:
+    """Prepared tensor-core rating of ONE item table (reference ``main.py:413-426`` rates every
+    user batch against the same propagated table): the bf16 UMMA tiles + item norms are built once
+    (``prepare``), and the workspace -- sized for ``max_users`` per call -- is allocated once and
+    reused by every user batch of a sweep."""
+
+    def __init__(self, n_items, d, device, max_users):
+        lib = _lib.load()
+        self.n_items, self.d, self.max_users, self.dev = int(n_items), int(d), int(max_users), device
+        self.wsb = lib.lgcn_score_tc_workspace(self.max_users, self.n_items, self.d)
+        if self.wsb == 0:
+            raise _lib.LgcnError("tensor-core rating supports d = 64 or 128")
+        self.ws = torch.empty(self.wsb, dtype=torch.uint8, device=device)
+        self.prepared_for = None                      # (data_ptr, version) of the prepared table
+
+    @on_device
+    def prepare(self, F_item):
+        if F_item.shape != (self.n_items, self.d):
+            raise _lib.LgcnError("TcRater.prepare: item table shape changed")
+        COUNTERS["launches"] += 2
+        check(_lib.load().lgcn_score_tc_prepare(ptr(F_item), self.n_items, self.d, self.ws.data_ptr(),
+                                                self.wsb, stream_ptr(self.dev)))
+        self.prepared_for = (F_item.data_ptr(), F_item._version)
+
+    @on_device
+    def topk(self, F_user, F_item, users, mask_rowptr, mask_col, k, out_ids, out_sc, fail):
+        """Filter + exact refine of one user batch (<= max_users) into the given output slices."""
+        nu = users.numel()
+        if nu > self.max_users:
+            raise _lib.LgcnError("TcRater.topk: batch larger than the workspace was sized for")
+        lib = _lib.load()
+        COUNTERS["launches"] += lib.lgcn_score_tc_launches(nu, self.n_items)
+        check(lib.lgcn_score_tc_topk(ptr(F_user), ptr(F_item), ptr(users, "i64"), nu, self.n_items,
+                                     self.d, ptr(mask_rowptr, "i64", allow_none=True),
+                                     ptr(mask_col, "i32", allow_none=True), k, ptr(out_ids, "i32"),
+                                     ptr(out_sc), ptr(fail, "i32"), self.ws.data_ptr(), self.wsb,
+                                     stream_ptr(self.dev)))
+
+
+# users per tensor-core launch of a sweep: whole waves of 148 CTAs x 128 users (the CTAs of a wave
+# stream the same item tiles, so the table is read from DRAM once per wave)
+TC_WAVE_USERS = 148 * 128
+TC_BATCH_WAVES = int(os.environ.get("LGCN_TC_BATCH_WAVES", "4"))
+
+
+@on_device
+def score_topk(F_user, F_item, users, mask_rowptr=None, mask_col=None, k=20, tensor_cores=None,
+               rater=None, batch_users=None):
     """Full-rank scores + train mask + top-k (reference ``main.py:420-426``).
     Returns (ids int32 [nu,k], scores fp32 [nu,k]); ids are exactly those of fp32 sequential-FMA
-    scoring.  Large catalogues go through the tcgen05 filter + exact re-score; users whose
-    result is not certified exact are re-run by the exact kernel."""
+    scoring.  Large catalogues go through the tcgen05 filter + exact re-score in user batches of
+    ``batch_users`` (one prepared table and one workspace for the whole sweep: pass a
+    :class:`TcRater` to keep them across calls); users whose result is not certified exact are
+    re-run by the exact kernel at the end (one host sync per sweep)."""
     nu = users.numel()
     d = F_user.shape[1]
     n_items = F_item.shape[0]
@@ -356,24 +458,29 @@ def score_topk(F_user, F_item, users, mask_rowptr=None, mask_col=None, k=20, ten
         tensor_cores = d in (64, 128) and n_items >= TC_MIN_ITEMS and k <= 32
     if not tensor_cores or nu == 0:
         return score_topk_exact(F_user, F_item, users, mask_rowptr, mask_col, k)
-    lib = _lib.load()
-    wsb = lib.lgcn_score_tc_workspace(nu, n_items, d)
-    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    if batch_users is None:
+        batch_users = TC_WAVE_USERS * TC_BATCH_WAVES
+    batch_users = max(1, min(int(batch_users), nu))
+    if rater is None:
+        rater = TcRater(n_items, d, dev, batch_users)
+    elif (rater.n_items, rater.d) != (n_items, d):
+        raise _lib.LgcnError("score_topk: the rater was built for another table shape")
+    batch_users = min(batch_users, rater.max_users)
     ids = torch.empty((nu, k), dtype=torch.int32, device=dev)
     sc = torch.empty((nu, k), dtype=torch.float32, device=dev)
     fail = torch.empty(nu, dtype=torch.int32, device=dev)
-    st = stream_ptr(dev)
-    COUNTERS["launches"] += 3
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if PROFILE is not None else None
     if ev:
         ev[0].record()
-    check(lib.lgcn_score_tc_prepare(ptr(F_item), n_items, d, ws.data_ptr(), wsb, st))
+    if rater.prepared_for != (F_item.data_ptr(), F_item._version):
+        rater.prepare(F_item)
     if ev:
         ev[1].record()
-    check(lib.lgcn_score_tc_topk(ptr(F_user), ptr(F_item), ptr(users, "i64"), nu, n_items, d,
-                                 ptr(mask_rowptr, "i64", allow_none=True),
-                                 ptr(mask_col, "i32", allow_none=True), k, ptr(ids, "i32"), ptr(sc),
-                                 ptr(fail, "i32"), ws.data_ptr(), wsb, st))
+    for b0 in range(0, nu, batch_users):
+        b1 = min(nu, b0 + batch_users)
+        # mask_rowptr holds absolute offsets into mask_col, so a batch is a view of both arrays
+        mr = mask_rowptr[b0:b1 + 1] if mask_rowptr is not None else None
+        rater.topk(F_user, F_item, users[b0:b1], mr, mask_col, k, ids[b0:b1], sc[b0:b1], fail[b0:b1])
     if ev:
         ev[2].record()
         PROFILE.append(("score_tc_prepare", ev[0], ev[1]))
@@ -391,6 +498,7 @@ def score_topk(F_user, F_item, users, mask_rowptr=None, mask_col=None, k=20, ten
     return ids, sc
 
 
+@on_device
 def eval_metrics(topk_ids, targets, sums=None):
     """sums += [#hits, sum 1/log2(rank+2)] (reference ``main.py:430-438``)."""
     nu, k = topk_ids.shape
@@ -417,6 +525,10 @@ class PropagateFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_f):
+        if ctx.g.symmetric is False:
+            raise _lib.LgcnError(
+                "the backward pass reuses the forward CSR (A^T == A); this adjacency is not "
+                "symmetric -- the reference's D^-1/2 A D^-1/2 (main.py:304-331) always is")
         acc = propagate_backward(ctx.g, grad_f.contiguous(), ctx.n_layers)
         return (None, None) + tuple(torch.split(acc, ctx.sizes, dim=0))
 

@@ -33,7 +33,7 @@ typedef struct CUstream_st *lgcn_stream_t; /* == cudaStream_t */
 #define LGCN_API
 #endif
 
-#define LGCN_ABI_VERSION 4
+#define LGCN_ABI_VERSION 5
 
 #define LGCN_E_BAD_DIM   (-1) /* embedding dim not supported              */
 #define LGCN_E_BAD_ARG   (-2) /* null pointer / negative size / bad mode  */
@@ -50,11 +50,18 @@ LGCN_API const char *lgcn_error_string(int code);
  * ------------------------------------------------------------------------------------- */
 
 /* Row-major sorted COO (what main.py:334-336 hands to forward) -> CSR.
- * rowptr[n_rows+1], col[nnz] int32.  status[0] receives the number of adjacent pairs that
- * violate strict (row,col) ordering (0 == valid CSR order, no duplicates). */
+ * rowptr[n_rows+1], col[nnz] int32.  status[0] receives the number of entries that violate
+ * strict (row,col) ordering or lie outside [0,n_rows) x [0,n_cols) (0 == valid CSR order, no
+ * duplicates, every index in range). */
 LGCN_API int lgcn_csr_from_sorted_coo(const int64_t *coo_row, const int64_t *coo_col, int64_t nnz,
-                             int64_t n_rows, int32_t *rowptr, int32_t *col, int32_t *status,
-                             lgcn_stream_t stream);
+                             int64_t n_rows, int64_t n_cols, int32_t *rowptr, int32_t *col,
+                             int32_t *status, lgcn_stream_t stream);
+
+/* status[0] += number of idx[i] outside [lo, hi) -- the device-side form of the IndexError the
+ * reference's gathers raise for a bad batch / evaluation index (reference main.py:496-497,420).
+ * The caller zeroes status and reads it back when it wants the verdict. */
+LGCN_API int lgcn_check_indices(const int64_t *idx, int64_t n, int64_t lo, int64_t hi, int32_t *status,
+                       lgcn_stream_t stream);
 
 /* val[e] = fl32(fl32(dinv[row]*mult[e]) * dinv[col[e]])  (mult == NULL -> 1), the value
  * scipy produces at main.py:330-331.  dinv is computed by the caller with the same
@@ -164,6 +171,11 @@ LGCN_API size_t lgcn_sizeof_spmm_args(void);
  * the count (> 0) or a negative LGCN_E_* code. */
 LGCN_API int lgcn_spmm_launches(int64_t n_rows, int32_t d, int32_t n_long, int32_t flags,
                        int32_t *small_path);
+/* Host-only query: the name of the MAIN kernel lgcn_spmm selects for this shape / mode (what a
+ * profiler shows; bench.py labels its roofline with it).  sparse_x != 0: the call passes
+ * x_rowflag.  Writes a NUL-terminated string of at most buf_bytes bytes; returns 0 or LGCN_E_*. */
+LGCN_API int lgcn_spmm_kernel_name(int64_t n_rows, int32_t d, int32_t mode, int32_t flags,
+                          int32_t sparse_x, char *buf, size_t buf_bytes);
 
 /* ---------------------------------------------------------------------------------------
  * a4  Fused BPR + L2 step.
@@ -265,7 +277,14 @@ LGCN_API int lgcn_score_topk(const float *Fu, const float *Fi, const int64_t *us
  * CERTIFIED exact (k-th exact score within the bf16 error bound of the filter threshold);
  * the caller re-runs those through lgcn_score_topk.  lgcn_score_tc_prepare converts the item
  * table once per table (bf16, UMMA canonical tiles) into the head of the workspace. */
+/* A run with fewer user tiles than SMs (the reference rates 1024 users per batch, main.py:415)
+ * cuts the catalogue into item splits so that the chip is filled; every split keeps its own
+ * candidates, the ordered per-split lists are merged exactly and certified against the largest
+ * threshold of any split.  lgcn_score_tc_workspace(nu, ..) is enough for EVERY call with at most
+ * nu users (a sweep reuses one workspace and one prepared table for all of its user batches).
+ * lgcn_score_tc_launches: host-only, kernels one lgcn_score_tc_topk call launches (2 or 3). */
 LGCN_API size_t lgcn_score_tc_workspace(int64_t nu, int64_t n_items, int32_t d);
+LGCN_API int lgcn_score_tc_launches(int64_t nu, int64_t n_items);
 LGCN_API int lgcn_score_tc_prepare(const float *Fi, int64_t n_items, int32_t d, void *workspace,
                           size_t workspace_bytes, lgcn_stream_t stream);
 LGCN_API int lgcn_score_tc_topk(const float *Fu, const float *Fi, const int64_t *users, int64_t nu,

@@ -137,3 +137,26 @@ def test_amazon_shape_properties(dev):
     rp, cols, got = mr.cpu().numpy(), mc.cpu().numpy(), ids.cpu().numpy()
     for q in range(256):
         assert not set(got[q].tolist()) & set(cols[rp[q]:rp[q + 1]].tolist())
+
+
+def test_tc_batched_sweep_and_item_splits_match_exact_kernel(dev):
+    """A rating sweep in user batches (one prepared table + one workspace for all batches, ragged
+    last batch, per-batch views of the mask CSR) and the item-split runs of small batches (few
+    user tiles: the catalogue is cut into splits, per-split lists merged and certified) return
+    the exact kernel's ids and score bits."""
+    from gcn_recommendation_b200 import _lib, ops
+    Fu, Fi, users, mr, mc, _ = _case(dev, 1000, 40000, 128, seed=21)
+    eids, esc = ops.score_topk_exact(Fu, Fi, users, mr, mc, 20)
+    lib = _lib.load()
+    assert lib.lgcn_score_tc_launches(256, 40000) == 3 and lib.lgcn_score_tc_launches(148 * 128, 40000) == 2
+    rater = ops.TcRater(40000, 128, dev, 256)
+    for bu in (256, 1000, 128):
+        ids, sc = ops.score_topk(Fu, Fi, users, mr, mc, 20, tensor_cores=True,
+                                 rater=rater if bu <= 256 else None, batch_users=bu)
+        assert torch.equal(ids, eids), bu
+        assert torch.equal(sc.view(torch.int32), esc.view(torch.int32)), bu
+    assert rater.prepared_for is not None
+    # no mask, k = 5
+    ids, sc = ops.score_topk(Fu, Fi, users, None, None, 5, tensor_cores=True, batch_users=300)
+    eids, esc = ops.score_topk_exact(Fu, Fi, users, None, None, 5)
+    assert torch.equal(ids, eids) and torch.equal(sc.view(torch.int32), esc.view(torch.int32))
