@@ -120,9 +120,15 @@ def make_batches(tu, ti, num_items, n, seed, device=None, pin=False):
 # reference arm / cpu baseline: the oracle's torch port on the host cores
 # ----------------------------------------------------------------------------------------
 def cpu_reference(workload, steps, warmup, budget_s=150.0):
+    """Time the oracle's torch port (the reference's own library calls in the reference's
+    composition, oracle/torch_port.py) on the host cores: ``warmup`` untimed + ``steps`` timed full
+    training steps on the bounded sample graph of the workload.  Uses every host core it can --
+    torchrun exports OMP_NUM_THREADS=1 to its workers, which would throttle this arm,
+    so the intra-op thread count is set explicitly."""
     import torch
     from gcn_recommendation_b200 import synth
     from oracle.torch_port import TorchPort
+    torch.set_num_threads(os.cpu_count() or 1)
     sample, scale = CPU_SAMPLE[workload]
     U, I, B, total, d, K = synth.SHAPES[sample]
     inter = synth.generate(sample, seed=0)
@@ -147,7 +153,8 @@ def cpu_reference(workload, steps, warmup, budget_s=150.0):
                 cores=torch.get_num_threads(), host_cpus=os.cpu_count(), d=d, K=K,
                 sample_desc=(f"{len(times)} full train steps (fwd {K}x torch.sparse.mm + BPR + backward "
                              f"+ Adam, bs {BS}) of the oracle's torch port on the '{sample}' graph "
-                             f"(N={U + I + B}), time x{scale:g} (nnz ratio) x {steps_per_epoch} steps/epoch"))
+                             f"(N={U + I + B}), measured {step_s * 1e3:.1f} ms/step x{scale:g} (nnz ratio) "
+                             f"x {steps_per_epoch} steps/epoch"))
 
 
 def run_reference(args):
@@ -155,15 +162,21 @@ def run_reference(args):
     if rank != 0:
         return
     r = cpu_reference(args.workload, args.steps, args.warmup)
+    # ms_per_step is the MEASURED step on the sample graph (steps x ms_per_step is the timed region);
+    # value / extrapolated_value scale it to the workload by the nnz ratio (the full
+    # Amazon-shape step does not fit the host: 33.8 s per torch.sparse.mm, > 75 GB)
     line = {
         "impl": "reference", "metric": "lightgcn_epoch_s", "value": r["epoch_s"], "unit": "s",
         "n_gpus": args.gpus, "steps": r["steps_timed"], "warmup": args.warmup,
-        "ms_per_step": r["step_s"] * r["scale"] * 1e3, "higher_is_better": False,
+        "ms_per_step": r["step_s"] * 1e3, "scale": r["scale"], "extrapolated_value": r["epoch_s"],
+        "extrapolated_ms_per_step": r["step_s"] * r["scale"] * 1e3,
+        "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "batch": BS, "d": r["d"], "layers": r["K"],
-                   "steps_per_epoch": r["steps_per_epoch"], "cpu_sample": r["sample"]},
+                   "steps_per_epoch": r["steps_per_epoch"], "cpu_sample": r["sample"],
+                   "same_config": r["scale"] == 1.0},
         "cpu_baseline": {"value": r["epoch_s"], "unit": "s", "cores": r["cores"], "kind": "port",
-                         "sample": r["sample_desc"]},
+                         "sample": r["sample_desc"], "host_cpus": r["host_cpus"]},
         "e2e": {"value": r["epoch_s"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -178,7 +191,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     from gcn_recommendation_b200 import ops, synth
-    from gcn_recommendation_b200.engine import LightGCNEngine, build_mask_csr, xavier_uniform_table
+    from gcn_recommendation_b200.engine import LightGCNEngine, mask_csr_from_graph, xavier_uniform_table
     from gcn_recommendation_b200.graph import NormAdjCSR
 
     rank = int(os.environ.get("RANK", "0"))
@@ -313,11 +326,17 @@ def run_b200(args):
                         "achieved_gbs": by / 1e9 / (ms / 1e3)}
     peak, peak_src = _peaks()
     dom = "plain" if "plain" in kernels else sorted(kernels)[0]
-    traffic = None
+    # dram__bytes_read + dram__bytes_write per launch of THIS kernel from a committed ncu --set full
+    # capture, keyed by (workload, local width, mode); null when this configuration was never
+    # captured (no stale constant: VERDICT r01)
+    traffic = traffic_src = None
     tp = os.path.join(ROOT, "profiles", "spmm_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(f"{args.workload}:{dom}")
+    if os.path.exists(tp) and not (world > 1 and args.parallelism == "row"):
+        ent = json.load(open(tp)).get(f"{args.workload}:{d_local}:{dom}")
+        if ent:
+            traffic, traffic_src = ent["bytes"], ent["source"]
     roofline = {"bound": "hbm", "kernel": ops.spmm_kernel_name(g_local, d_local, dom),
+                "traffic_source": traffic_src,
                 "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_gb"] * 1e9,
@@ -334,39 +353,79 @@ def run_b200(args):
     barrier()
     e2e_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
 
-    # ---- full-rank eval on a sample of users ----------------------------------------------
+    # ---- full-rank eval sweep (BASELINE configs[4]; reference main.py:404-439) -----------------
+    # A fixed number of validation users per GPU (default 1 M: 53 waves of 148 x 128 users, so the
+    # timed region is seconds long and is held against the SUSTAINED bf16 peak), rated in user
+    # batches against the full catalogue with the train items masked; users sharded over the ranks.
     ev = None
-    if args.eval_users > 0 and (world == 1 or args.parallelism == "feature"):
-        nu = min(args.eval_users * world, U)                         # fixed users per GPU
+    if args.eval_users > 0:
+        nu = min(args.eval_users * world, int(vu.numel()))
         nu -= nu % world
         per = nu // world
         eu = vu[rank * per:(rank + 1) * per].contiguous()           # this rank's users
         tg = vi[rank * per:(rank + 1) * per].contiguous()
-        mr, mc = build_mask_csr(eu.cpu().numpy(), tu_h.numpy(), ti_h.numpy(), U, dev)
-        eng.evaluate(eu[:64], tg[:64], mr[:65].contiguous(), mc, 20)          # warm-up
+        mr, mc = mask_csr_from_graph(csr, eu, U)                     # mask = training interactions
+        eng.evaluate(eu[:256], tg[:256], mr[:257].contiguous(), mc, 20)       # warm-up
+        ops.STATS["tc_users"] = ops.STATS["tc_fallback_users"] = 0
         barrier()
         ev0.record()
         rec, ndcg, _ = eng.evaluate(eu, tg, mr, mc, 20)
         ev1.record()
         barrier()
         ems = max_over_ranks(ev0.elapsed_time(ev1))
+        ev_clock = ClockSampler("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
+        barrier()
         ev0.record()
         eng.evaluate(eu, tg, mr, mc, 20, propagate=False)            # rating only (table already final)
         ev1.record()
         barrier()
         rms = max_over_ranks(ev0.elapsed_time(ev1))
-        ev = {"users_per_s": nu / (ems / 1e3), "users": nu, "items": I, "ms": ems,
+        ev_clocks = ev_clock.stop() if ev_clock else None
+        tfl = 2.0 * nu * I * d / (rms / 1e3) / 1e12
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+            os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+        fb = torch.tensor([ops.STATS["tc_users"], ops.STATS["tc_fallback_users"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(fb)
+        ev = {"users_per_s": nu / (ems / 1e3), "users": nu, "users_per_gpu": per, "items": I, "ms": ems,
               "rating_only_users_per_s": nu / (rms / 1e3), "rating_only_ms": rms,
-              "rating_only_tflops": 2.0 * nu * I * d / (rms / 1e3) / 1e12,
-              "recall@20": rec, "ndcg@20": ndcg, "tc_stats": dict(ops.STATS),
-              "note": "users_per_s: one propagation (+ all-gather of the final table when sharded) + "
-                      "rating of a user sample; rating_only: tcgen05 bf16 filter with fused mask and "
-                      "128-candidate heaps + exact fp32 re-score/top-20 over the full catalogue "
-                      "(what a full-population sweep amortises to); users sharded over the ranks"}
+              "rating_only_tflops": tfl,
+              "tensor_frac_of_sustained_peak": tfl / (pk["bf16_tflops_sustained"] * world),
+              "tensor_frac_of_burst_peak": tfl / (pk["bf16_tflops"] * world),
+              "recall@20": rec, "ndcg@20": ndcg,
+              "tc_users": int(fb[0].item()), "tc_fallback_users": int(fb[1].item()),
+              "user_batch": ops.TC_WAVE_USERS * ops.TC_BATCH_WAVES, "clocks": ev_clocks,
+              "note": "users_per_s: one propagation (+ all-gather of the final table when sharded) + the "
+                      "rating sweep; rating_only: the sweep alone = tcgen05 bf16 filter with fused train mask "
+                      "and candidate heaps + exact fp32 re-score / top-20 (ids are those of fp32 scoring; "
+                      "tc_fallback_users had to be re-run by the exact kernel)"}
+
+    # ---- cross-N witness: must agree to <= 1e-6 relative at every N / parallelism --
+    # fp64 sum and L2 norm of the full parameter table after all steps of this run, and the top-20
+    # of 256 fixed validation users (ids hashed; the score sum is the rounding-tolerant form: a
+    # near-tie may swap two ids between runs, the scores cannot move)
+    import zlib
+    P_full = eng._full_table() if world > 1 else eng.P
+    ps = P_full.double()
+    witness = {"param_sum": float(ps.sum().item()), "param_l2": float(ps.pow(2).sum().sqrt().item())}
+    del ps, P_full
+    wu = vu[:256].contiguous()
+    wmr, wmc = mask_csr_from_graph(csr, wu, U)
+    if world > 1:
+        Ff = eng.gather_final_table()
+        wids, wsc = ops.score_topk(Ff[:U], Ff[U:U + I], wu, wmr, wmc, 20)
+        del Ff
+    else:
+        wids, wsc = eng.rate_topk(wu, wmr, wmc, 20)
+    wids_h = wids.cpu().numpy()
+    witness.update(top20_ids_crc32=int(zlib.crc32(np.ascontiguousarray(wids_h).tobytes())),
+                   top5_ids_crc32=int(zlib.crc32(np.ascontiguousarray(wids_h[:, :5]).tobytes())),
+                   top20_score_sum=float(wsc.double().sum().item()),
+                   steps_applied=int(eng.step_dev.item()))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(args.workload, 3, 1, budget_s=40.0)
+        r = cpu_reference(args.workload, args.steps, args.warmup, budget_s=60.0)   # same leg as --impl reference
         cpu = {"value": r["epoch_s"], "unit": "s", "cores": r["cores"], "kind": "port",
                "sample": r["sample_desc"], "host_cpus": r["host_cpus"]}
 
@@ -388,7 +447,7 @@ def run_b200(args):
                     "h2d_bytes_per_step": 3 * BS * 8, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "roofline": roofline, "kernels": kernels, "eval": ev, "cpu_baseline": cpu,
-            "loss": last_loss,
+            "loss": last_loss, "witness": witness,
         }
         os.write(out_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
@@ -406,7 +465,8 @@ def main():
     ap.add_argument("--fusion", action="store_true",
                     help="LightGCN_Fusion: 768-d side embeddings projected and merged into the item "
                          "rows of layer 0 (BASELINE.json configs[3]); item-sharded on N > 1 GPUs")
-    ap.add_argument("--eval-users", type=int, default=18944)
+    ap.add_argument("--eval-users", type=int, default=1 << 20,
+                    help="validation users rated PER GPU in the eval sweep (0 = skip)")
     ap.add_argument("--parallelism", default="feature", choices=["feature", "row"],
                     help="multi-GPU partitioning: feature columns (no propagation collectives) or "
                          "graph rows with a per-layer all-gather (north-star layout)")

@@ -137,14 +137,13 @@ class FeatureShardedEngine(LightGCNEngine):
         self._allreduce_sum(f["gb"])
         self._rows_to_cols(self.GE_rows, f["g_eid"])
 
-    def _bpr(self, F, gp_includes_gf):
-        u, p, n = self.b_users, self.b_pos, self.b_neg
-        ops.bpr_partial(F, self.P, u, p, n, self.U, self.dots)
-        self._allreduce(self.dots)                     # the only collective of the step
-        ops.bpr_apply(F, self.P, u, p, n, self.U, self.lam, self.dots,
-                      grad_scale=1.0 / (self.K + 1), gF=self.G1, gP=self.G2,
-                      gp_includes_gf=gp_includes_gf, sample_ws=self.sample_ws, loss_out=self.loss,
-                      rowflag=self.rowflag)
+    def _bpr_term(self, F, pos, neg, item_offset, lam, scale, gp_includes_gf, loss_out):
+        u = self.b_users
+        ops.bpr_partial(F, self.P, u, pos, neg, item_offset, self.dots)
+        self._allreduce(self.dots)                     # the only collective of the term
+        ops.bpr_apply(F, self.P, u, pos, neg, item_offset, lam, self.dots, grad_scale=scale,
+                      gF=self.G1, gP=self.G2, gp_includes_gf=gp_includes_gf, sample_ws=self.sample_ws,
+                      loss_out=loss_out, rowflag=self.rowflag)
 
     # ---- reference-format checkpoints from column shards -------------------------
     def _gather_columns(self, local):
@@ -276,6 +275,7 @@ class RowShardedEngine:
             if int(self.idx_status.item()) != 0:
                 raise IndexError("batch indices are out of range")
             self._checked_bs = bs
+        self._F_full = None                        # it is a view of a ping-pong buffer
         self.propagate()
         F_full = self._gather(self.Floc, self.Xa if (K - 1) % 2 == 0 else self.Xb)
         # every rank forms the whole batch redundantly; gradients land in full-size scratch

@@ -29,7 +29,17 @@ _CHECK_ALWAYS = os.environ.get("LGCN_CHECK_INDICES", "0") == "1"
 def build_mask_csr(eval_users, train_user, train_item, num_users, device=None):
     """Per-evaluated-user ascending train-item lists as CSR over the position in ``eval_users``
     (what ``train_df.groupby('user_idx')['item_idx'].apply(list)`` feeds the mask loop of
-    reference ``main.py:407,422-424``).  Host numpy; returns int64 rowptr / int32 col tensors."""
+    reference ``main.py:407,422-424``).  Returns int64 rowptr / int32 col tensors.  Host numpy
+    arrays are processed on the host; CUDA tensors stay on the device (sort + searchsorted)."""
+    if isinstance(train_user, torch.Tensor) and train_user.is_cuda:
+        dev = train_user.device
+        tu, ti = train_user.to(torch.int64), train_item.to(torch.int64)
+        n_items = int(ti.max().item()) + 1 if ti.numel() else 1
+        key = torch.sort(tu * n_items + ti).values
+        start = torch.searchsorted(key, torch.arange(num_users + 1, device=dev, dtype=torch.int64) * n_items)
+        eu = torch.as_tensor(eval_users, device=dev).to(torch.int64)
+        rp, cc = ops._sub_csr(start, (key % n_items).to(torch.int32), eu)
+        return rp, cc
     tu = np.ascontiguousarray(train_user, np.int64)
     ti = np.ascontiguousarray(train_item, np.int64)
     order = np.lexsort((ti, tu))
@@ -45,6 +55,14 @@ def build_mask_csr(eval_users, train_user, train_item, num_users, device=None):
     if device is not None:
         rp, cc = rp.to(device), cc.to(device)
     return rp, cc
+
+
+def mask_csr_from_graph(g, eval_users, num_users):
+    """The same mask lists read off the graph itself: rows [0, U) of the adjacency ARE the users'
+    train items (columns U + item, ascending), so validation-time masks (mask = training
+    interactions, reference ``main.py:407,545``) need no second sort.  Device ops only."""
+    eu = torch.as_tensor(eval_users, device=g.device).to(torch.int64)
+    return ops._sub_csr(g.rowptr.to(torch.int64), g.col - int(num_users), eu)
 
 
 def xavier_uniform_table(rows_list, d, device, generator=None):
@@ -70,7 +88,8 @@ class LightGCNEngine:
     """
 
     def __init__(self, g, num_users, num_items, num_brands, n_layers, table, lr=1e-3,
-                 weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, fusion=None, batch_size=2048):
+                 weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, fusion=None, batch_size=2048,
+                 item_to_brand=None, brand_loss_weight=0.0):
         self.g = g
         self.U, self.I, self.B = int(num_users), int(num_items), int(num_brands)
         self.N = self.U + self.I + self.B
@@ -104,6 +123,18 @@ class LightGCNEngine:
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self.idx_status = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.bs = int(batch_size)
+        # optional brand / author BPR term (reference main.py:382-391): item -> brand lookup + weight
+        self.brand_w = float(brand_loss_weight)
+        self.item_brand = None
+        if self.brand_w != 0.0:
+            if item_to_brand is None or self.B <= 0:
+                raise LgcnError("brand_loss_weight needs item_to_brand and num_brands > 0")
+            self.item_brand = torch.as_tensor(item_to_brand, device=self.dev).to(torch.int64).contiguous()
+            if self.item_brand.numel() != self.I:
+                raise LgcnError("item_to_brand must have one entry per item")
+            if self.item_brand.numel() and (int(self.item_brand.min()) < 0 or int(self.item_brand.max()) >= self.B):
+                raise IndexError("item_to_brand index out of range")
+            self.loss_brand = torch.zeros(1, dtype=torch.float32, device=self.dev)
         # Sparse first-hop output + flagged second hop: pays when the tables stream from HBM
         # (Amazon shape: 4.6 + 5.2 -> 1.8 + 3.5 ms); on L2-resident graphs the extra flag lookups
         # only lengthen a latency-bound kernel (Gowalla shape: 0.66 -> 0.78 ms per step).
@@ -127,6 +158,8 @@ class LightGCNEngine:
         self.b_pos = torch.zeros(bs, dtype=torch.int64, device=self.dev)
         self.b_neg = torch.zeros(bs, dtype=torch.int64, device=self.dev)
         self.sample_ws = torch.empty(2 * bs, dtype=torch.float32, device=self.dev)
+        self.b_bpos = torch.zeros(bs, dtype=torch.int64, device=self.dev)     # brands of pos / neg items
+        self.b_bneg = torch.zeros(bs, dtype=torch.int64, device=self.dev)
         self._graph = None
 
     def _init_fusion(self, f):
@@ -143,6 +176,8 @@ class LightGCNEngine:
         """Kernels of THIS library launched per training step (for bench.py's gpu_launches)."""
         per_spmm = ops.spmm_launches(self.g, self.d)
         n = 2 * self.K * per_spmm + 2 + 1 + 1          # spmm fwd+bwd, bpr(+reduce), tick, zero
+        if self.brand_w != 0.0:
+            n += 2 + 1                                 # brand term (+reduce), its zero_rows
         if self.fusion is not None:
             n += 1 + 2 + 5                             # proj fwd, proj bwd (2), 5 adam launches
         return n
@@ -181,13 +216,27 @@ class LightGCNEngine:
         U, I = self.U, self.I
         return F[:U], F[U:U + I], F[U + I:], self.P[:U], self.P[U:U + I]
 
+    def _bpr_term(self, F, pos, neg, item_offset, lam, scale, gp_includes_gf, loss_out):
+        """One BPR term over (b_users, pos, neg) rows at ``item_offset``: loss into ``loss_out``,
+        ``scale * dL/dF`` scattered into G1 and the regulariser gradient (+ the same dL/dF when
+        ``gp_includes_gf``) into G2, touched rows flagged."""
+        ops.bpr_fused(F, self.P, self.b_users, pos, neg, item_offset, lam, grad_scale=scale,
+                      gF=self.G1, gP=self.G2, gp_includes_gf=gp_includes_gf, sample_ws=self.sample_ws,
+                      loss_out=loss_out, rowflag=self.rowflag)
+
     def _bpr(self, F, gp_includes_gf):
         """Loss + scatter of dL/dF (scaled by 1/(K+1)) into G1 and of the regulariser gradient
-        into G2 for the staged batch (reference ``main.py:496-497,515-525``)."""
-        ops.bpr_fused(F, self.P, self.b_users, self.b_pos, self.b_neg, self.U, self.lam,
-                      grad_scale=1.0 / (self.K + 1), gF=self.G1, gP=self.G2,
-                      gp_includes_gf=gp_includes_gf, sample_ws=self.sample_ws, loss_out=self.loss,
-                      rowflag=self.rowflag)
+        into G2 for the staged batch (reference ``main.py:496-497,515-525``); with
+        ``brand_loss_weight`` also the brand term of ``main.py:382-391,401`` (same kernel over the
+        brand rows of the batch's items, no regulariser, weighted)."""
+        scale = 1.0 / (self.K + 1)
+        self._bpr_term(F, self.b_pos, self.b_neg, self.U, self.lam, scale, gp_includes_gf, self.loss)
+        if self.brand_w != 0.0:
+            torch.index_select(self.item_brand, 0, self.b_pos, out=self.b_bpos)
+            torch.index_select(self.item_brand, 0, self.b_neg, out=self.b_bneg)
+            self._bpr_term(F, self.b_bpos, self.b_bneg, self.U + self.I, 0.0, scale * self.brand_w,
+                           gp_includes_gf, self.loss_brand)
+            self.loss.add_(self.loss_brand, alpha=self.brand_w)
 
     def _step_body(self):
         g, K, U, I = self.g, self.K, self.U, self.I
@@ -225,6 +274,8 @@ class LightGCNEngine:
             ops.adam(f["W"], f["gW"], f["mW"], f["vW"], sc, **kw)
             ops.adam(f["b"], f["gb"], f["mb"], f["vb"], sc, **kw)
         ops.zero_rows(self.G1, self.G2, u, p, n, U, rowflag=self.rowflag)
+        if self.brand_w != 0.0:
+            ops.zero_rows(self.G1, self.G2, u, self.b_bpos, self.b_bneg, U + I, rowflag=self.rowflag)
 
     # ---- public --------------------------------------------------------------------------
     def capture(self):
@@ -295,7 +346,7 @@ class LightGCNEngine:
             self._step_body()
         return self.loss
 
-    _BATCH_BUFFERS = ("b_users", "b_pos", "b_neg")
+    _BATCH_BUFFERS = ("b_users", "b_pos", "b_neg", "b_bpos", "b_bneg")
 
     def _tail_step(self, users, pos, neg, bs):
         full = {k: getattr(self, k) for k in self._BATCH_BUFFERS + ("sample_ws",) + self._extra_batch_buffers()}

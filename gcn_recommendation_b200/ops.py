@@ -393,7 +393,7 @@ def _sub_csr(rowptr, col, idx):
     torch.cumsum(cnt, 0, out=rp[1:])
     src = torch.repeat_interleave(rowptr[idx] - rp[:-1], cnt) + torch.arange(int(rp[-1].item()),
                                                                             device=rowptr.device)
-    return rp, col[src].contiguous()
+    return rp, col[src].to(torch.int32).contiguous()
 
 
 class TcRater:

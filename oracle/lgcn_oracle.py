@@ -158,6 +158,26 @@ def bpr_loss(F, E0_user, E0_item, users, pos, neg, num_users, lam, want_grads=Tr
     return float(loss), gF, gU, gI
 
 
+def bpr_brand_term(F, users, pos, neg, item_to_brand, num_users, num_items):
+    """The brand / author BPR term of reference ``main.py:382-391``:
+    ``-mean(log(sigmoid(<F_u, F_brand[b(pos)]> - <F_u, F_brand[b(neg)]>) + 1e-8))`` with
+    ``b = item_to_brand`` (the lookup ``main.py:499-511`` intends).  Same arithmetic as the item
+    term with the brand block as the "item" table and no regulariser, so the same C loop serves:
+    item offset = U + I, lambda = 0.  Returns (term, gF) -- unweighted; the caller applies
+    ``brand_loss_weight`` (``main.py:401``)."""
+    F = _f32(F)
+    i2b = _i64(item_to_brand)
+    bp, bn = i2b[_i64(pos)], i2b[_i64(neg)]
+    off = int(num_users) + int(num_items)
+    gF = np.zeros_like(F)
+    dummy_u = np.zeros_like(F[:num_users])          # lambda = 0: regulariser rows are never used
+    dummy_b = np.zeros_like(F[off:])
+    term = lib().lgcn_oracle_bpr(_p(F), _p(dummy_u), _p(dummy_b), _p(_i64(users)), _p(bp), _p(bn),
+                                 ctypes.c_int64(len(bp)), ctypes.c_int32(F.shape[1]),
+                                 ctypes.c_int64(off), ctypes.c_float(0.0), _p(gF), None, None)
+    return float(term), gF
+
+
 # ----------------------------------------------------------------------------------------
 # a5  Adam                              reference main.py:469,526
 # ----------------------------------------------------------------------------------------

@@ -71,7 +71,7 @@ def _batches(rng, tu, ti, num_items, bs, n_steps):
 
 
 def run_case(main, model_cls, name, shape, d, K, bs, n_steps, use_brand, fusion, seed,
-             min_degree=3, n_dup=0):
+             min_degree=3, n_dup=0, brand_loss_weight=None):
     """``min_degree=2`` leaves users without any training edge after the test / validation
     hold-outs (isolated nodes: degree 0 -> d = 0, reference main.py:329); ``n_dup`` appends
     repeated (user, item) rows to train.parquet (multiplicity > 1 in the adjacency, summed by the
@@ -104,6 +104,11 @@ def run_case(main, model_cls, name, shape, d, K, bs, n_steps, use_brand, fusion,
                            "num_brands": nb}, f)
             golden["item_brand_item"] = ib["item_idx"].values
             golden["item_brand_brand"] = ib["brand_idx"].values
+            i2b = np.zeros(inter.num_items, np.int64)
+            i2b[ib["item_idx"].values] = ib["brand_idx"].values
+            golden["item_to_brand"] = i2b
+            if brand_loss_weight is not None:
+                golden["brand_loss_weight"] = np.float64(brand_loss_weight)
         dev = torch.device("cpu")
         (train_df, val_df, test_df, U, I, B, adj, item_brand_df) = main.load_preprocessed_data(
             ddir, dev, use_brand=use_brand, debug=False)
@@ -142,8 +147,18 @@ def run_case(main, model_cls, name, shape, d, K, bs, n_steps, use_brand, fusion,
         users, pos, neg = torch.from_numpy(u), torch.from_numpy(p), torch.from_numpy(n)
         opt.zero_grad()
         fu, fi, fb, u0, i0 = model(adj, use_brand=use_brand)
-        loss = main.bpr_loss_reg(fu[users], fi[pos], fi[neg], u0[users], i0[pos], i0[neg],
-                                 cfg.weight_decay)
+        if brand_loss_weight is None:
+            loss = main.bpr_loss_reg(fu[users], fi[pos], fi[neg], u0[users], i0[pos], i0[neg],
+                                     cfg.weight_decay)
+        else:
+            # the brand / author BPR term of reference main.py:382-391, fed the way main.py:499-522
+            # intends (item -> brand lookup of the batch's positive and negative items); the
+            # reference's train() never defines item_to_brand, so the FUNCTION is what is pinned
+            i2b = torch.from_numpy(golden["item_to_brand"])
+            loss = main.bpr_loss_reg(fu[users], fi[pos], fi[neg], u0[users], i0[pos], i0[neg],
+                                     cfg.weight_decay, brand_loss=True, final_brand_emb=fb,
+                                     pos_item_brand_idx=i2b[pos], neg_item_brand_idx=i2b[neg],
+                                     brand_loss_weight=brand_loss_weight)
         loss.backward()
         if s == 0:
             for k, prm in model.named_parameters():
@@ -286,6 +301,10 @@ def run_config_scale_case(main, model_cls, name, shape, d, K, bs, n_steps, seed,
 def main_():
     main, lg, lf = _import_reference()
     os.makedirs(os.path.join(REPO, "tests", "golden"), exist_ok=True)
+    if "--brand-loss" in sys.argv:         # the brand BPR term on the tripartite graph
+        run_case(main, lg.LightGCN, "tiny_brandloss_d64_k3", "tiny", 64, 3, 256, 3, True, False, 2,
+                 brand_loss_weight=0.1)
+        return
     if "--config-scale" in sys.argv:       # ~2 min of CPU: the Gowalla-shape run (configs[1])
         run_config_scale_case(main, lg.LightGCN, "gowalla_lightgcn_d64_k3", "gowalla", 64, 3, 2048, 20, 0)
         return

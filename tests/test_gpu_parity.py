@@ -364,6 +364,62 @@ def test_engine_training_matches_reference(golden, dev, case, use_graph):
     assert not eng.G1.any() and not eng.G2.any()
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_engine_brand_bpr_term_matches_reference(golden, dev, use_graph):
+    """engine with the brand / author BPR term (reference main.py:382-391,401) on the
+    tripartite graph against the run recorded from the reference's own bpr_loss_reg."""
+    case = "tiny_brandloss_d64_k3"
+    g = golden(case)
+    model = _model(g, case, dev)
+    csr = _graph(g, dev)
+    eng = model.engine(csr, lr=float(g["lr"]), weight_decay=float(g["lam"]), batch_size=int(g["bs"]),
+                       item_to_brand=g["item_to_brand"], brand_loss_weight=float(g["brand_loss_weight"]))
+    losses = []
+    for s in range(len(g["losses"])):
+        u, p, n = (torch.from_numpy(g[k][s]) for k in ("batch_users", "batch_pos", "batch_neg"))
+        losses.append(float(eng.bpr_step(u, p, n, use_graph=use_graph).item()))
+        if s == 0:
+            sd = model.state_dict()
+            for k in sd:
+                mx, fro = rel_err(sd[k].cpu().numpy(), g["step1/" + k])
+                assert mx < 1e-3 and fro < TOL, (k, mx, fro)
+    assert np.allclose(losses, g["losses"], rtol=2e-5, atol=0), (losses, g["losses"])
+    sd = model.state_dict()
+    for k in sd:
+        mx, fro = rel_err(sd[k].cpu().numpy(), g["final/" + k])
+        assert mx < 1e-3 and fro < 1e-5, (k, mx, fro)
+    assert not eng.G1.any() and not eng.G2.any() and not eng.rowflag.any()
+
+
+def test_engine_tail_batch_keeps_the_captured_graph_and_bad_indices_raise(golden, dev):
+    """A shorter last batch runs eagerly on views of the staging buffers (no re-capture, the
+    reference's DataLoader delivers one per epoch, main.py:462-464); out-of-range batch indices
+    raise IndexError like the reference's gathers (main.py:496-497)."""
+    case = "tiny_lightgcn_d64_k3"
+    g = golden(case)
+    bs = int(g["bs"])
+    out = []
+    for graph in (False, True):
+        model = _model(g, case, dev)
+        eng = model.engine(_graph(g, dev), lr=float(g["lr"]), weight_decay=float(g["lam"]), batch_size=bs)
+        u, p, n = (torch.from_numpy(g[k][0]) for k in ("batch_users", "batch_pos", "batch_neg"))
+        eng.bpr_step(u, p, n, use_graph=graph)
+        captured = eng._graph
+        l2 = eng.bpr_step(u[:100], p[:100], n[:100], use_graph=graph).item()
+        assert eng._graph is captured and eng.bs == bs
+        l3 = eng.bpr_step(u, p, n, use_graph=graph).item()
+        out.append((l2, l3, eng.P.clone()))
+        assert not eng.G1.any() and not eng.G2.any()
+    assert out[0][0] == pytest.approx(out[1][0], rel=1e-6) and out[0][1] == pytest.approx(out[1][1], rel=1e-6)
+    assert rel_err(out[0][2].cpu().numpy(), out[1][2].cpu().numpy())[1] < 1e-6
+    bad = torch.from_numpy(g["batch_users"][0]).clone()
+    bad[5] = int(g["num_users"])
+    model = _model(g, case, dev)
+    eng = model.engine(_graph(g, dev), batch_size=bs)
+    with pytest.raises(IndexError):
+        eng.bpr_step(bad, torch.from_numpy(g["batch_pos"][0]), torch.from_numpy(g["batch_neg"][0]), use_graph=False)
+
+
 @pytest.mark.parametrize("fusion", [False, True])
 def test_engine_sparse_backward_hops_are_bit_identical(golden, dev, fusion):
     """The sparse-gradient shortcuts (first Horner hop writes only its non-zero rows, second hop

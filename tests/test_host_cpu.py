@@ -243,3 +243,26 @@ def test_parameter_packing_keeps_identity_and_state_dict_keys():
     with pytest.raises(ValueError):
         LightGCN_Fusion(10, 20, 1, cfg)
     del opt
+
+
+def test_epoch_history_csv_is_the_reference_format(tmp_path):
+    """`<model>_epoch_history.csv` byte-identical to the reference Logger's
+    ``DataFrame.to_csv(index=False)`` (reference main.py:106-126), and a committed result file of
+    the reference parses back into the same rows."""
+    import pandas as pd
+
+    from gcn_recommendation_b200.history import EpochHistory, logger_name
+    rows = [(5, 0.4604123456789, 0.1151, 0.0615), (10, 1 / 3, 0.6622, 0.34220000000000006),
+            (150, 2.5e-05, 0.0, 1.0)]
+    name = logger_name("LightGCN", False, True)
+    assert name == "LightGCN_no_brand_pretrained"
+    h = EpochHistory(str(tmp_path), name)
+    assert h.save() is None and not os.path.exists(h.path)          # main.py:114-116
+    for r in rows:
+        h.log_epoch_metrics(*r)
+    path = h.save()
+    assert os.path.basename(path) == "LightGCN_no_brand_pretrained_epoch_history.csv"
+    ref = tmp_path / "ref.csv"
+    pd.DataFrame({"epoch": [r[0] for r in rows], "avg_loss": [r[1] for r in rows],
+                  "recall": [r[2] for r in rows], "ndcg": [r[3] for r in rows]}).to_csv(ref, index=False)
+    assert open(path, "rb").read() == open(ref, "rb").read()

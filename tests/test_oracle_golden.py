@@ -269,3 +269,37 @@ def test_config_scale_golden_pins_the_oracle(golden):
     ids, sc = orc.score_topk(F[:U], F[U:U + I], users[:n], mr, mc, 20)
     assert np.allclose(sc, g["eval/topk_scores"][:n], rtol=2e-5, atol=1e-9)
     assert near_tie_rows_ok(ids, g["eval/topk_ids"][:n], g["eval/topk_scores"][:n]) <= n // 50
+
+
+def test_brand_bpr_term_vs_reference(golden):
+    """the brand / author BPR term of reference main.py:382-391 (recorded by calling
+    the reference's own bpr_loss_reg with brand_loss=True on the tripartite graph): oracle loss,
+    first-step gradients and the 3-step loss curve."""
+    g = golden("tiny_brandloss_d64_k3")
+    a = _adj(g)
+    U, I, K = int(g["num_users"]), int(g["num_items"]), int(g["K"])
+    w, lam = float(g["brand_loss_weight"]), float(g["lam"])
+    names = ["user_embedding.weight", "item_embedding.weight", "brand_embedding.weight"]
+    P = {k: g["init/" + k].copy() for k in names}
+    M = {k: np.zeros_like(P[k]) for k in names}
+    V = {k: np.zeros_like(P[k]) for k in names}
+    for s in range(len(g["losses"])):
+        E0 = np.concatenate([P[k] for k in names], 0)
+        F, _ = orc.propagate(a["rowptr"], a["col"], a["val"], E0, K)
+        u, p, n = g["batch_users"][s], g["batch_pos"][s], g["batch_neg"][s]
+        loss, gF, gU, gI = orc.bpr_loss(F, P[names[0]], P[names[1]], u, p, n, U, lam)
+        term, gFb = orc.bpr_brand_term(F, u, p, n, g["item_to_brand"], U, I)
+        loss += w * term
+        assert abs(loss - g["losses"][s]) <= 2e-5 * abs(g["losses"][s]), (s, loss, g["losses"][s])
+        dE0 = orc.propagate_backward(a["rowptr"], a["col"], a["val"], gF + np.float32(w) * gFb, K)
+        G = {names[0]: dE0[:U] + gU, names[1]: dE0[U:U + I] + gI, names[2]: dE0[U + I:]}
+        if s == 0:
+            for k in names:
+                mx, fro = rel_err(G[k], g["grad1/" + k])
+                assert mx < TOL and fro < TOL, (k, mx, fro)
+            assert np.abs(g["grad1/" + names[2]]).max() > 0          # the brand rows do get gradients
+        for k in names:
+            orc.adam_step(P[k], G[k], M[k], V[k], s + 1, lr=float(g["lr"]))
+    for k in names:
+        mx, fro = rel_err(P[k], g["final/" + k])
+        assert mx < 1e-3 and fro < 1e-5, (k, mx, fro)
