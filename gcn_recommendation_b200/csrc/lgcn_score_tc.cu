@@ -36,12 +36,19 @@ namespace tc {
 
 constexpr int MT = 128;        // users per CTA (UMMA M)
 constexpr int NT = 128;        // items per tile (UMMA N)
-constexpr int NSTAGE = 3;      // item-tile ring
-constexpr int CAND = 96;       // candidates kept per user (all epilogue groups together)
-constexpr int NB = 4;          // TMEM accumulator buffers == epilogue groups (tile t -> group t % NB)
-constexpr int GCAND = CAND / NB;             // heap entries per (user, group)
-constexpr int kThreads = 64 + NB * 128;      // warp 0: copy producer, warp 1: MMA issuer, then NB
-                                             // epilogue groups of 4 warps (one per TMEM lane quadrant)
+#ifndef LGCN_TC_NSTAGE
+#define LGCN_TC_NSTAGE 3
+#endif
+#ifndef LGCN_TC_CAND
+#define LGCN_TC_CAND 96
+#endif
+constexpr int NSTAGE = LGCN_TC_NSTAGE;   // item-tile ring
+constexpr int CAND = LGCN_TC_CAND;       // candidates kept per user (all epilogue groups together)
+constexpr int NB = 4;          // TMEM accumulator buffers (tile t -> accumulator t % NB) == candidate heaps per user
+constexpr int GCAND = CAND / NB;             // heap entries per (user, epilogue group, column half)
+constexpr int kThreads = 64 + NB * 128;      // warp 0: copy producer, warp 1: MMA issuer, then two
+                                             // epilogue groups of 8 warps (2 column halves x 4 TMEM lane quadrants)
+static_assert(NB == 4, "two epilogue groups x two accumulators each");
 constexpr int TMEM_COLS = NB * 128;          // NB 128-column fp32 accumulators (all 512 columns)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -234,7 +241,7 @@ score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ us
     // ---- one-time setup ------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(smem_u32(&sm.full[s]), 1); mbar_init(smem_u32(&sm.empty[s]), 1); }
-        for (int b = 0; b < NB; ++b) { mbar_init(smem_u32(&sm.tfull[b]), 1); mbar_init(smem_u32(&sm.tempty[b]), 4); }
+        for (int b = 0; b < NB; ++b) { mbar_init(smem_u32(&sm.tfull[b]), 1); mbar_init(smem_u32(&sm.tempty[b]), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -299,13 +306,23 @@ score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ us
             }
         }
     } else {
-        // ===== epilogue: group g owns tiles t = g (mod NB); thread <-> user <-> TMEM lane =====
-        const int g = (warp - 2) >> 2;                // epilogue group == accumulator buffer
+        // ===== epilogue: two groups of 8 warps; group g owns tiles t = g (mod 2) and therefore TWO
+        // accumulators (t mod 4) that it fills and drains alternately: while it works on tile t the
+        // MMA already runs into its other accumulator (tile t + 2), so neither side waits out the
+        // commit -> wake-up -> arrive round trip (ncu r02 on the one-accumulator-per-group design:
+        // the MMA thread never waited for a tile to land, it waited for `tempty`, and the epilogue
+        // warps spun on `tfull` half of the time -- a latency-bound handshake, tensor pipe 32 %).
+        // Inside a group the tile's 128 columns are split between two warps per TMEM lane quadrant
+        // (thread <-> user <-> lane; half h takes columns [64h, 64h + 64)), each with its own heap.
+        const int ew = warp - 2;
+        const int g = ew >> 3;                        // epilogue group: tiles t = g (mod 2)
+        const int half = (ew >> 2) & 1;               // column half of the tile
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+        const int hsel = g * 2 + half;                // heap / threshold slot of this (group, half)
         const int u = quad * 32 + lane;
         const int64_t q = q0 + u;
-        float *hs = &sm.heap_s[g][0][0];
-        int *hi = &sm.heap_i[g][0][0];
+        float *hs = &sm.heap_s[hsel][0][0];
+        int *hi = &sm.heap_i[hsel][0][0];
         float tau = -FLT_MAX;
         // c_u = 1.05 * 2^-8 * |u|: key = s + c_u |v| bounds the exact score from above
         float cu = 0.f;
@@ -319,31 +336,33 @@ score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ us
             }
             cu = 1.05f * 0.00390625f * sqrtf(n2) * 1.000001f;
         }
-        const float4 *wn4 = reinterpret_cast<const float4 *>(wnorm);
-        float4 wn_next = g < n_tiles ? __ldg(wn4 + t0 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // window norms: two 32-item windows per (tile, half)
+        const float2 *wn2 = reinterpret_cast<const float2 *>(wnorm);
+        float2 wn_next = g < n_tiles ? __ldg(wn2 + (size_t)(t0 + g) * 2 + half) : make_float2(0.f, 0.f);
         int64_t mb = 0, me = 0;
         if (mask_rowptr && q < nu) { mb = mask_rowptr[q]; me = mask_rowptr[q + 1]; }
         int next_masked = (mb < me) ? __ldg(mask_col + mb) : 0x7fffffff;
-        for (int t = g; t < n_tiles; t += NB) {
-            const float4 wn_t = wn_next;                   // window norms of this tile, fetched a tile ahead
-            if (t + NB < n_tiles) wn_next = __ldg(wn4 + t0 + t + NB);
-            mbar_wait(smem_u32(&sm.tfull[g]), ((t / NB) & 1));
+        for (int t = g; t < n_tiles; t += 2) {
+            const int b = t % NB;                          // accumulator of this tile
+            const float2 wn_t = wn_next;                   // window norms of this half, fetched a tile ahead
+            if (t + 2 < n_tiles) wn_next = __ldg(wn2 + (size_t)(t0 + t + 2) * 2 + half);
+            mbar_wait(smem_u32(&sm.tfull[b]), ((t / NB) & 1));
             tc_fence_after();
-            const int tile_item0 = (t0 + t) * NT;
-            // this group sees every NB-th tile: advance the mask cursor to the tile start
-            while (next_masked < tile_item0) {            // register compare; loads only on advance
+            const int half_item0 = (t0 + t) * NT + half * 64;
+            // this warp sees one half of every second tile: advance the mask cursor to its start
+            while (next_masked < half_item0) {            // register compare; loads only on advance
                 ++mb;
                 next_masked = (mb < me) ? __ldg(mask_col + mb) : 0x7fffffff;
             }
 #pragma unroll 1
-            for (int c = 0; c < NT / 32; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t raw[32];
-                tc_ld32_issue(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * NT + c * 32), raw);
+                tc_ld32_issue(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * NT + half * 64 + c * 32), raw);
                 tc_ld_wait();
                 float v[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-                const int item0 = tile_item0 + c * 32;
+                const int item0 = half_item0 + c * 32;
                 // the user's train items inside this 32-column window (sorted list, cursor)
                 while (next_masked < item0 + 32) {
                     const int j = next_masked - item0;
@@ -365,31 +384,32 @@ score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ us
 #pragma unroll
                 for (int i = 0; i < 4; ++i) m4[i] = fmaxf(m8[2 * i], m8[2 * i + 1]);
                 const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-                const float wn = c == 0 ? wn_t.x : (c == 1 ? wn_t.y : (c == 2 ? wn_t.z : wn_t.w));
-                if (fmaf(cu, wn, mx) > tau) {                 // rare once the heap has warmed up
-                    const float4 *vn4 = reinterpret_cast<const float4 *>(vnorm + item0);
+                const float wn = c == 0 ? wn_t.x : wn_t.y;
+                // Rare for one thread once its heap has warmed up -- but a tile is released only when
+                // all of its 8 warps are through, and with ~10 % of the warp-windows in here most
+                // tiles wait for one (ncu r02): keep this path free of loads.  A score can only enter
+                // the heap if it beats the threshold even with the window's LARGEST norm, so the
+                // item's own norm is fetched for those few scores alone (its key <= that bound).
+                if (fmaf(cu, wn, mx) > tau) {
 #pragma unroll
-                    for (int i4 = 0; i4 < 8; ++i4) {
-                        const float4 n = __ldg(vn4 + i4);
-                        const float key0 = fmaf(cu, n.x, v[4 * i4]), key1 = fmaf(cu, n.y, v[4 * i4 + 1]);
-                        const float key2 = fmaf(cu, n.z, v[4 * i4 + 2]), key3 = fmaf(cu, n.w, v[4 * i4 + 3]);
-                        if (key0 > tau) tau = heap_push(hs, hi, u, key0, item0 + 4 * i4);
-                        if (key1 > tau) tau = heap_push(hs, hi, u, key1, item0 + 4 * i4 + 1);
-                        if (key2 > tau) tau = heap_push(hs, hi, u, key2, item0 + 4 * i4 + 2);
-                        if (key3 > tau) tau = heap_push(hs, hi, u, key3, item0 + 4 * i4 + 3);
+                    for (int i = 0; i < 32; ++i) {
+                        if (fmaf(cu, wn, v[i]) > tau) {
+                            const float key = fmaf(cu, __ldg(vnorm + item0 + i), v[i]);
+                            if (key > tau) tau = heap_push(hs, hi, u, key, item0 + i);
+                        }
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&sm.tempty[g]));
+            if (lane == 0) mbar_arrive(smem_u32(&sm.tempty[b]));
         }
         if (q < nu) {
             for (int k = 0; k < GCAND; ++k) {
-                cand_s[q * CAND + g * GCAND + k] = hs[k * MT + u];
-                cand_i[q * CAND + g * GCAND + k] = hi[k * MT + u];
+                cand_s[q * CAND + hsel * GCAND + k] = hs[k * MT + u];
+                cand_i[q * CAND + hsel * GCAND + k] = hi[k * MT + u];
             }
-            tau_out[q * NB + g] = tau;
+            tau_out[q * NB + hsel] = tau;
         }
     }
     tc_fence_before();

@@ -462,17 +462,28 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #ifndef LGCN_RING_R
 #define LGCN_RING_R 8
 #endif
+#ifndef LGCN_RING_S_NARROW
+#define LGCN_RING_S_NARROW 8           // ring slots of tables narrower than LGCN_RING_S lanes (d = 16)
+#endif
 constexpr int kRingWarps = LGCN_RING_WARPS;
 
 template <int D>
 struct RingCfg {
     using G = RowGeom<D>;
     static constexpr int R = G::LANES < LGCN_RING_R ? G::LANES : LGCN_RING_R;   // one row end per lane
-    static constexpr int S = G::LANES < LGCN_RING_S ? G::LANES : LGCN_RING_S;   // ring slots (power of 2)
+    // ring slots (power of 2).  A worker of a narrow table has few lanes (4 at d = 16), and with
+    // one {col,val} per lane per tile the ring could not be deeper than that: 3 gathers of 64 bytes
+    // in flight per worker left the DRAM pipe half empty (ncu r01: 54 % DRAM, 30 warps / SM = the
+    // 32-CTA limit).  So the tile is decoupled from the lane count: TL stream entries per tile,
+    // EPL = TL / LANES of them per lane, and the ring is S deep whatever the width.
+    static constexpr int S = G::LANES < LGCN_RING_S ? LGCN_RING_S_NARROW : LGCN_RING_S;
+    static constexpr int TL = G::LANES > S ? G::LANES : S;                       // entries per tile
+    static constexpr int EPL = TL / G::LANES;                                    // entries per lane
+    static constexpr int SL = G::LANES < S ? G::LANES : S;                       // live-list batch
     static constexpr int WORKERS = kRingWarps * G::GROUPS;
     static constexpr int ROWS_PER_CTA = WORKERS * R;
     static constexpr size_t SMEM = (size_t)WORKERS * (R + S) * D * sizeof(float);
-    static_assert((S & (S - 1)) == 0 && S >= 2 && S <= G::LANES, "ring depth");
+    static_assert((S & (S - 1)) == 0 && S >= 2 && TL % S == 0 && TL % G::LANES == 0, "ring depth");
     static_assert(R % 4 == 0, "chunk rows");
 };
 
@@ -481,7 +492,7 @@ __global__ void __launch_bounds__(kRingWarps * 32)
 spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
     using G = RowGeom<D>;
     using C = RingCfg<D>;
-    constexpr int L = G::LANES, S = C::S;
+    constexpr int L = G::LANES, S = C::S, TL = C::TL, EPL = C::EPL;
     const uint64_t pol = HINT ? policy_evict_first() : 0ull;
     const GatherPolicy gpol = gather_policy<HINT>(a.flags, pol);
     extern __shared__ __align__(16) float ring_smem[];
@@ -528,14 +539,26 @@ spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
     const char *xb = reinterpret_cast<const char *>(a.x + sub * 4);
     const int2 *cvp = reinterpret_cast<const int2 *>(a.colval) + chunk_beg;
     const int2 z2 = make_int2(0, 0);
-    int2 cvA = sub < n_e ? ld_cv<HINT>(cvp + sub, pol) : z2;                 // entries [t, t+L)
-    int2 cvB = L + sub < n_e ? ld_cv<HINT>(cvp + L + sub, pol) : z2;         // [t+L, t+2L)
-    int2 cvC = 2 * L + sub < n_e ? ld_cv<HINT>(cvp + 2 * L + sub, pol) : z2; // [t+2L, t+3L)
+    // {col,val} tiles of TL stream entries: lane `sub` holds entries sub*EPL .. sub*EPL+EPL-1
+    struct Tile { int2 e[EPL]; };
+    auto load_tile = [&](int t0) {
+        Tile T;
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+            const int i = t0 + sub * EPL + k;
+            T.e[k] = i < n_e ? ld_cv<HINT>(cvp + i, pol) : z2;
+        }
+        return T;
+    };
+    Tile cvA = load_tile(0);                                                 // entries [t, t+TL)
+    Tile cvB = load_tile(TL);                                                // [t+TL, t+2TL)
+    Tile cvC = load_tile(2 * TL);                                            // [t+2TL, t+3TL)
     // Gather of stream entry t+JJ (tile-relative index JJ is a compile-time constant, so the source
     // lane of the shuffle, the tile register and the ring slot are all immediates).
     auto issue = [&](int t, auto jj_c) {
         constexpr int JJ = decltype(jj_c)::value;
-        const int cr = __shfl_sync(0xffffffffu, JJ < L ? cvA.x : cvB.x, JJ % L, L);
+        constexpr int JT = JJ % TL;
+        const int cr = __shfl_sync(0xffffffffu, JJ < TL ? cvA.e[JT % EPL].x : cvB.e[JT % EPL].x, JT / EPL, L);
         if (t + JJ < n_e) {
             const char *src = xb + (uint64_t)(uint32_t)(cr & LGCN_COL_MASK) * (D * 4);
             const uint32_t dst = ring_s + (uint32_t)(JJ % S) * (D * 4);
@@ -559,16 +582,16 @@ spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
     int cur = 0;                                          // row (within the chunk) being summed
     int cur_end = __shfl_sync(0xffffffffu, my_end, 0, L); // first stream entry past that row
 
-    for (int t = 0; t < max_n; t += L) {                  // cvA = entries [t,t+L), cvB = [t+L,t+2L)
+    for (int t = 0; t < max_n; t += TL) {                 // cvA = entries [t,t+TL), cvB = [t+TL,t+2TL)
         bool done = false;
-        static_for<L>([&](auto j_c) {
+        static_for<TL>([&](auto j_c) {
             constexpr int J = decltype(j_c)::value;
             if (done) return;
             const int e = t + J;
             if (e >= max_n) { done = true; return; }      // warp-uniform
             issue(t, std::integral_constant<int, J + S - 1>{});
             cp_async_wait<S - 1>();                       // this lane's bytes of entry e have landed
-            const float wj = __int_as_float(__shfl_sync(0xffffffffu, cvA.y, J, L));
+            const float wj = __int_as_float(__shfl_sync(0xffffffffu, cvA.e[J % EPL].y, J / EPL, L));
             const bool live = e < n_e;
 
             // leave every row that ends at or before e: the finished sum (zeros for the empty rows
@@ -596,7 +619,7 @@ spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
         });
         cvA = cvB;                                        // consume pointer leaves its tile
         cvB = cvC;
-        cvC = t + 3 * L + sub < n_e ? ld_cv<HINT>(cvp + t + 3 * L + sub, pol) : z2;
+        cvC = load_tile(t + 3 * TL);
     }
     cp_async_wait<0>();
     // rows cur .. nvr-1: the last summed row, then trailing empty rows
@@ -628,7 +651,7 @@ __global__ void __launch_bounds__(kRingWarps * 32)
 spmm_live_kernel(const __grid_constant__ lgcn_spmm_args a) {
     using G = RowGeom<D>;
     using C = RingCfg<D>;
-    constexpr int L = G::LANES, S = C::S;
+    constexpr int L = G::LANES, S = C::SL;
     const uint64_t pol = HINT ? policy_evict_first() : 0ull;
     extern __shared__ __align__(16) float ring_smem[];
     const int lane = threadIdx.x & 31;

@@ -32,6 +32,28 @@ if len(sys.argv) > 4:
     d = int(sys.argv[4])
 inter = synth.generate_device(workload, dev, seed=0)
 tu, ti, _, _ = synth.split_validation_device(inter)
+if os.environ.get("LGCN_RELABEL"):
+    # experiment: relabel the USERS so that users sharing an item are neighbours
+    # in the row order -> the item row they gather is re-used while it is still in L2.  Keys:
+    #   coldest      : the user's lowest-degree item
+    #   hot:<n>      : the user's highest-degree item outside the <n> hottest (those stay L2-resident)
+    rl = os.environ["LGCN_RELABEL"]
+    deg_i = torch.bincount(ti, minlength=I)
+    if rl == "coldest":
+        score = deg_i[ti] * I + ti
+    else:
+        nres = int(rl.split(":")[1])
+        rank = torch.empty(I, dtype=torch.int64, device=dev)
+        rank[torch.argsort(deg_i, descending=True, stable=True)] = torch.arange(I, device=dev)
+        r = rank[ti]
+        score = torch.where(r >= nres, r, r + 10 * I)
+    key = torch.full((U,), 1 << 62, dtype=torch.int64, device=dev).scatter_reduce_(0, tu, score, "amin")
+    order = torch.argsort(key, stable=True)
+    newid = torch.empty(U, dtype=torch.int64, device=dev)
+    newid[order] = torch.arange(U, device=dev)
+    tu = newid[tu]
+    print(f"relabelled users by {rl}")
+    del deg_i, score, key, order, newid
 g = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev)
 del inter, tu, ti
 N = U + I + B

@@ -93,12 +93,13 @@ def test_gowalla_engine_matches_the_reference_run(gowalla, dev):
     eng = model.engine(csr, lr=float(g["lr"]), weight_decay=float(g["lam"]), batch_size=int(g["bs"]))
     rows = g["sample_rows"]
     F = eng.propagate().cpu().numpy()
-    short = np.diff(csr.rowptr.cpu().numpy()) <= csr.long_row_threshold
+    # (not bit-exact here: rows longer than the threshold are summed segment-wise, and from the
+    # second layer on every row gathers some of them; a single SpMM is bit-exact on the sequential
+    # rows -- test_gowalla_shape_properties)
+    assert csr.n_long > 0
     for part, off in (("user", 0), ("item", U)):
-        got, ref = F[off + rows], g["fwd_sample/" + part]
-        sh = short[off + rows]
-        assert np.array_equal(_bits(got[sh]), _bits(ref[sh])), "short rows must be bit-exact"
-        assert rel_err(got, ref)[0] < TOL
+        mx, fro = rel_err(F[off + rows], g["fwd_sample/" + part])
+        assert mx < TOL and fro < TOL, (part, mx, fro)
     losses = []
     for s in range(len(g["losses"])):
         u, p, n = (torch.from_numpy(g[k][s].astype(np.int64)).pin_memory()
@@ -191,10 +192,12 @@ def test_amazon_16th_engine_step_and_topk_vs_oracle(dev):
     P0 = table.cpu().numpy().copy()
     eng = LightGCNEngine(csr, U, I, B, K, table, batch_size=2048)
     assert eng.sparse_hops
-    F_ref, _ = orc.propagate(a["rowptr"], a["col"], a["val"], P0, K)
-    F = eng.propagate().cpu().numpy()
+    F_ref, layers = orc.propagate(a["rowptr"], a["col"], a["val"], P0, K)
     short = np.diff(a["rowptr"]) <= csr.long_row_threshold
-    assert np.array_equal(_bits(F[short]), _bits(F_ref[short])), "sequential rows must be bit-exact"
+    Y1 = ops.spmm(csr, eng.P).cpu().numpy()                 # one layer: sequential rows bit-exact
+    assert np.array_equal(_bits(Y1[short]), _bits(layers[1][short])), "sequential rows must be bit-exact"
+    assert rel_err(Y1, layers[1])[0] < TOL
+    F = eng.propagate().cpu().numpy()                       # K layers + mean: long rows feed every row
     mx, fro = rel_err(F, F_ref)
     assert mx < TOL and fro < TOL
 

@@ -406,7 +406,8 @@ def test_engine_tail_batch_keeps_the_captured_graph_and_bad_indices_raise(golden
         eng.bpr_step(u, p, n, use_graph=graph)
         captured = eng._graph
         l2 = eng.bpr_step(u[:100], p[:100], n[:100], use_graph=graph).item()
-        assert eng._graph is captured and eng.bs == bs
+        assert eng._graph is captured                    # the captured step survives the tail batch
+        assert eng.bs == (bs if graph else 100)          # eager mode simply re-sizes the staging
         l3 = eng.bpr_step(u, p, n, use_graph=graph).item()
         out.append((l2, l3, eng.P.clone()))
         assert not eng.G1.any() and not eng.G2.any()
@@ -418,6 +419,51 @@ def test_engine_tail_batch_keeps_the_captured_graph_and_bad_indices_raise(golden
     eng = model.engine(_graph(g, dev), batch_size=bs)
     with pytest.raises(IndexError):
         eng.bpr_step(bad, torch.from_numpy(g["batch_pos"][0]), torch.from_numpy(g["batch_neg"][0]), use_graph=False)
+
+
+@pytest.mark.parametrize("case", ["tiny_lightgcn_d64_k3", "tiny_fusion_d64_k3"])
+def test_checkpoint_round_trip_in_the_reference_format(golden, dev, case, tmp_path):
+    """SURVEY 8f-4 on the GPU: train with the engine, ``torch.save(engine.state_dict())`` (what
+    reference main.py:550 writes), reload it the way ``main.test`` does (main.py:571:
+    ``model.load_state_dict(torch.load(path))``) into a fresh drop-in module AND into a fresh
+    engine: same keys / order as the reference, parameters equal to the reference's final ones,
+    and evaluation from the reloaded module reproduces ``main.evaluate``'s metrics."""
+    from gcn_recommendation_b200 import ops
+    from gcn_recommendation_b200.engine import build_mask_csr
+    orc = _orc()
+    g = golden(case)
+    model = _model(g, case, dev)
+    csr = _graph(g, dev)
+    eng = model.engine(csr, lr=float(g["lr"]), weight_decay=float(g["lam"]), batch_size=int(g["bs"]))
+    for s in range(len(g["losses"])):
+        eng.bpr_step(*(torch.from_numpy(g[k][s]) for k in ("batch_users", "batch_pos", "batch_neg")), use_graph=False)
+    path = str(tmp_path / "best_model.pth")
+    torch.save(eng.state_dict(), path)
+    sd = torch.load(path)
+    assert list(sd.keys()) == [k[5:] for k in g if k.startswith("init/")]
+    fresh = _model(g, case, dev)                       # golden init again
+    fresh.load_state_dict(sd)                          # reference main.py:571
+    for k, v in fresh.state_dict().items():
+        if k == "item_content_embedding":
+            assert torch.equal(v.cpu(), torch.from_numpy(g["init/" + k]))
+            continue
+        assert torch.equal(v.cpu(), sd[k])
+        mx, fro = rel_err(v.cpu().numpy(), g["final/" + k])
+        assert mx < 1e-3 and fro < 1e-5, (k, mx, fro)
+    eng2 = _model(g, case, dev).engine(csr, batch_size=int(g["bs"]))
+    eng2.load_state_dict(sd)
+    assert torch.equal(eng2.P, eng.P)
+    if "fusion" in case:
+        assert torch.equal(eng2.fusion["W"], eng.fusion["W"]) and torch.equal(eng2.fusion["b"], eng.fusion["b"])
+    users, targets = orc.eval_pairs(g["val_user"], g["val_item"])
+    mr, mc = build_mask_csr(users, g["train_user"], g["train_item"], int(g["num_users"]), dev)
+    rec, ndcg, _ = eng2.evaluate(_t(users, dev, torch.int64), _t(targets, dev, torch.int64), mr, mc, 20)
+    rec1, ndcg1, _ = eng.evaluate(_t(users, dev, torch.int64), _t(targets, dev, torch.int64), mr, mc, 20)
+    assert (rec, ndcg) == (rec1, ndcg1)                # the reloaded engine IS the trained one
+    # parameters trained here differ from the reference's in the last bits: a fp32 near-tie at
+    # rank 20 may move one user's hit, nothing more
+    assert abs(rec - float(g["eval/recall"])) <= 1.0 / len(users) + 1e-12
+    assert abs(ndcg - float(g["eval/ndcg"])) <= 1.0 / len(users) + 1e-12
 
 
 @pytest.mark.parametrize("fusion", [False, True])
