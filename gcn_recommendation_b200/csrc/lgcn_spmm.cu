@@ -494,7 +494,10 @@ spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
     using C = RingCfg<D>;
     constexpr int L = G::LANES, S = C::S, TL = C::TL, EPL = C::EPL;
     const uint64_t pol = HINT ? policy_evict_first() : 0ull;
-    const GatherPolicy gpol = gather_policy<HINT>(a.flags, pol);
+    // per-gather L2 classes only where they were measured to matter (512-byte rows and wider:
+    // profiles/r01_hot_columns_sweep.txt shows no effect at d = 16 / 32, where the walk is issue bound)
+    constexpr bool GHINT = HINT && D >= 64;
+    const GatherPolicy gpol = gather_policy<GHINT>(a.flags, pol);
     extern __shared__ __align__(16) float ring_smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -562,7 +565,7 @@ spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
         if (t + JJ < n_e) {
             const char *src = xb + (uint64_t)(uint32_t)(cr & LGCN_COL_MASK) * (D * 4);
             const uint32_t dst = ring_s + (uint32_t)(JJ % S) * (D * 4);
-            if (HINT) {
+            if (GHINT) {
                 const uint64_t gp = pick_policy(gpol, cr);
 #pragma unroll
                 for (int v = 0; v < G::VEC; ++v) cp_async16_hint(dst + v * L * 16, src + v * L * 16, gp);

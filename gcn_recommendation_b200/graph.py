@@ -17,11 +17,12 @@ import torch
 
 from . import _lib
 
-LONG_ROW_THRESHOLD = 256
-SEG_LEN = 128
+LONG_ROW_THRESHOLD_SMALL = 64       # L2-resident (latency-bound) graphs, see _plan defaults below
+SEG_LEN_SMALL = 128
 LONG_ROW_THRESHOLD_LARGE = 512
 SEG_LEN_LARGE = 512
 SMALL_GRAPH_ROWS = 1_000_000
+TINY_GRAPH_ROWS = 8192
 
 
 class NormAdjCSR:
@@ -44,14 +45,22 @@ class NormAdjCSR:
             long_row_threshold = int(os.environ["LGCN_LONG_ROW_THRESHOLD"])      # tuning hook
             seg_len = int(os.environ.get("LGCN_SEG_LEN", max(long_row_threshold // 2, 8)))
         if long_row_threshold is None:
-            # small graphs are latency bound: shorter sequential chains, more workers
+            # small graphs are latency bound: a launch lasts as long as its longest sequential row,
+            # so rows above 64 entries go to the (balanced) segment workers; 128-entry segments keep
+            # the number of partials the hottest row's combine has to chain low.  Gowalla-shape step:
+            # 128/64 0.564 ms, 64/64 0.458, 32/64 0.454, 64/128 0.429
+            # (profiles/r02_gowalla_threshold_sweep.txt)
             small = self.n_rows < SMALL_GRAPH_ROWS
             # large graphs (ring kernel: gathers stay pipelined across row boundaries, so long
             # sequential rows are cheap): 512/512 measured best at the Amazon shape (5.06 ms vs
             # 5.23 ms for 256/128); it also leaves fewer rows on the not-bit-exact segment path
-            long_row_threshold = LONG_ROW_THRESHOLD // 2 if small else LONG_ROW_THRESHOLD_LARGE
-            seg_len = seg_len or (SEG_LEN // 2 if small else SEG_LEN_LARGE)
-        self._plan_long_rows(long_row_threshold, seg_len or SEG_LEN, rowptr_host)
+            long_row_threshold = LONG_ROW_THRESHOLD_SMALL if small else LONG_ROW_THRESHOLD_LARGE
+            seg_len = seg_len or (SEG_LEN_SMALL if small else SEG_LEN_LARGE)
+            if self.n_rows < TINY_GRAPH_ROWS:
+                # a few thousand rows are one partial wave: nothing to balance, and the sequential
+                # (bit-exact) path keeps rows of up to 128 entries (round-1 plan 128 / 64)
+                long_row_threshold, seg_len = 128, 64
+        self._plan_long_rows(long_row_threshold, seg_len or SEG_LEN_SMALL, rowptr_host)
 
     # ---- kernel layout (once per graph) ------------------------------------------------
     def _plan_long_rows(self, threshold, seg_len, rowptr_host=None):
