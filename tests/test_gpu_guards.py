@@ -35,6 +35,7 @@ class Guarded:
     def __init__(self, dev):
         self.dev = dev
         self.bufs = []
+        self.keep = []
 
     def _alloc(self, n, dtype, guard_value):
         buf = torch.empty(n + 2 * PAD, dtype=dtype, device=self.dev)
@@ -63,6 +64,7 @@ class Guarded:
             poison = 1
         buf = self._alloc(n, t.dtype, poison)
         buf[PAD:PAD + n] = t.flatten().to(self.dev)
+        self.keep.append(buf)                      # raw data_ptr() users must not outlive the buffer
         return buf[PAD:PAD + n].view(t.shape)
 
     def check(self):

@@ -266,3 +266,59 @@ def test_epoch_history_csv_is_the_reference_format(tmp_path):
     pd.DataFrame({"epoch": [r[0] for r in rows], "avg_loss": [r[1] for r in rows],
                   "recall": [r[2] for r in rows], "ndcg": [r[3] for r in rows]}).to_csv(ref, index=False)
     assert open(path, "rb").read() == open(ref, "rb").read()
+
+
+def test_host_only_plan_queries():
+    """Host-only entry points of the C ABI (no GPU needed): kernel selection names, launch counts,
+    the scoring workspace that must serve every smaller batch, item-split launch counts."""
+    import ctypes
+
+    from gcn_recommendation_b200 import _lib
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(128)
+
+    def name(n_rows, d, mode, flags=0, sparse_x=0):
+        assert lib.lgcn_spmm_kernel_name(n_rows, d, mode, flags, sparse_x, buf, 128) == 0
+        return buf.value.decode()
+
+    assert name(70_840, 64, _lib.SPMM_PLAIN) == "spmm_chunk_kernel<64,plain,4-row chunks,nohints>"
+    assert name(14_700_001, 128, _lib.SPMM_PLAIN, _lib.SPMM_F_STREAM_HINTS) == "spmm_ring_kernel<128,plain,hints>"
+    assert name(14_700_001, 16, _lib.SPMM_MEAN, _lib.SPMM_F_STREAM_HINTS) == "spmm_ring_kernel<16,mean,hints>"
+    assert name(14_700_001, 128, _lib.SPMM_ADAM, _lib.SPMM_F_STREAM_HINTS).startswith("spmm_chunk_kernel<128,adam,16-row")
+    assert name(14_700_001, 128, _lib.SPMM_ADD, _lib.SPMM_F_STREAM_HINTS, 1) == "spmm_live_kernel<128,hints>"
+    assert lib.lgcn_spmm_kernel_name(10, 48, 0, 0, 0, buf, 128) == -1                   # LGCN_E_BAD_DIM
+    assert lib.lgcn_spmm_kernel_name(10, 64, 9, 0, 0, buf, 128) == -2                   # LGCN_E_BAD_ARG
+    # scoring: whole waves run unsplit (2 launches), small batches are item-split (+ merge)
+    assert lib.lgcn_score_tc_launches(148 * 128, 4_400_000) == 2
+    assert lib.lgcn_score_tc_launches(1024, 4_400_000) == 3
+    assert lib.lgcn_score_tc_launches(1024, 2000) == 2                                 # too few tiles to split
+    big = lib.lgcn_score_tc_workspace(75_776, 4_400_000, 128)
+    for nu in (1, 128, 1024, 18_944, 75_776):
+        assert lib.lgcn_score_tc_workspace(nu, 4_400_000, 128) <= big
+    assert lib.lgcn_score_tc_workspace(100, 1000, 48) == 0                              # unsupported width
+
+
+def test_mask_csr_builders_agree():
+    """``mask_csr_from_graph`` (validation-time masks read off the graph's user rows) equals the
+    sort-based ``build_mask_csr`` and the oracle's ``mask_csr`` (reference main.py:407)."""
+    import numpy as np
+    import torch
+
+    from gcn_recommendation_b200 import synth
+    from gcn_recommendation_b200.engine import build_mask_csr, mask_csr_from_graph
+    from oracle import lgcn_oracle as orc
+    inter = synth.generate("tiny", seed=3)
+    tu, ti, vu, vi = inter.split_validation()
+    U, I, B = inter.num_users, inter.num_items, inter.num_brands
+    a = orc.build_norm_adj(tu, ti, U, I, B)
+    g = type("G", (), {})()
+    g.device = torch.device("cpu")
+    g.rowptr = torch.from_numpy(a["rowptr"].astype(np.int32))
+    g.col = torch.from_numpy(a["col"])
+    users = np.asarray([5, 0, 119, 7, 7], np.int64)
+    rp1, c1 = mask_csr_from_graph(g, users, U)
+    rp2, c2 = build_mask_csr(users, tu, ti, U)
+    rp3, c3 = orc.mask_csr(users, tu, ti, U)
+    assert np.array_equal(rp1.numpy(), rp3) and np.array_equal(c1.numpy(), c3)
+    assert np.array_equal(rp2.numpy(), rp3) and np.array_equal(c2.numpy(), c3)
+    assert c1.dtype == torch.int32 and rp1.dtype == torch.int64
