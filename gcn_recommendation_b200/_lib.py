@@ -21,6 +21,7 @@ SPMM_F_NO_RING = 2
 SPMM_F_BIG_PATH = 4
 SPMM_F_COLD_FIRST = 8
 SPMM_F_FORCE_RING = 16
+SPMM_F_NO_PREFETCH = 32
 BPR_GP_INCLUDES_GF, BPR_NO_GRAD = 1, 2
 ABI_VERSION = 5
 

@@ -74,26 +74,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE_%=:\n\t}"
         ::"r"(bar), "r"(parity) : "memory");
 }
-// same wait, but the thread is SUSPENDED by the hardware for up to `ns` nanoseconds per attempt
-// (woken when the phase completes) instead of re-issuing the poll every few cycles: 16 polling
-// epilogue warps otherwise take issue slots from the warps that are working on a tile
-__device__ __forceinline__ void mbar_wait_suspend(uint32_t bar, uint32_t parity, uint32_t ns) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAITS_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra DONES_%=;\n\t"
-        "bra WAITS_%=;\n\t"
-        "DONES_%=:\n\t}"
-        ::"r"(bar), "r"(parity), "r"(ns) : "memory");
-}
-#ifndef LGCN_TC_WAIT_NS
-#define LGCN_TC_WAIT_NS 0               // 0 = plain try_wait polling
-#endif
-__device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
-    if (LGCN_TC_WAIT_NS > 0) mbar_wait_suspend(bar, parity, LGCN_TC_WAIT_NS);
-    else mbar_wait(bar, parity);
-}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -300,7 +280,7 @@ score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ us
         if (lane == 0) {
             for (int t = 0; t < n_tiles; ++t) {
                 const int s = t % NSTAGE;
-                mbar_wait_long(smem_u32(&sm.empty[s]), ((t / NSTAGE) & 1) ^ 1);
+                mbar_wait(smem_u32(&sm.empty[s]), ((t / NSTAGE) & 1) ^ 1);
                 mbar_expect_tx(smem_u32(&sm.full[s]), TILE_BYTES);
                 bulk_g2s(smem_u32(&sm.B[s][0]), Bt + (size_t)(t0 + t) * (NT * D), TILE_BYTES, smem_u32(&sm.full[s]));
             }
@@ -311,7 +291,7 @@ score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ us
             const uint32_t a_base = smem_u32(&sm.A[0]);
             for (int t = 0; t < n_tiles; ++t) {
                 const int s = t % NSTAGE, b = t % NB;
-                mbar_wait_long(smem_u32(&sm.tempty[b]), ((t / NB) & 1) ^ 1);    // epilogue drained this accumulator
+                mbar_wait(smem_u32(&sm.tempty[b]), ((t / NB) & 1) ^ 1);    // epilogue drained this accumulator
                 mbar_wait(smem_u32(&sm.full[s]), (t / NSTAGE) & 1);        // tile landed in smem
                 tc_fence_after();
                 const uint32_t b_base = smem_u32(&sm.B[s][0]);
@@ -366,7 +346,7 @@ score_filter_kernel(const float *__restrict__ Fu, const int64_t *__restrict__ us
             const int b = t % NB;                          // accumulator of this tile
             const float2 wn_t = wn_next;                   // window norms of this half, fetched a tile ahead
             if (t + 2 < n_tiles) wn_next = __ldg(wn2 + (size_t)(t0 + t + 2) * 2 + half);
-            mbar_wait_long(smem_u32(&sm.tfull[b]), ((t / NB) & 1));
+            mbar_wait(smem_u32(&sm.tfull[b]), ((t / NB) & 1));
             tc_fence_after();
             const int half_item0 = (t0 + t) * NT + half * 64;
             // this warp sees one half of every second tile: advance the mask cursor to its start

@@ -98,6 +98,34 @@ __device__ __forceinline__ uint64_t pick_policy(const GatherPolicy &g, int col_r
     return col_raw < 0 ? g.last : ((col_raw & LGCN_COL_ONCE) ? g.first : g.mid);
 }
 
+// ---- L2 prefetch of the epilogue's operand rows ---------------------------------------------
+// A worker first walks its chunk's entries (gather phase), then streams the chunk's rows of the
+// epilogue operands (p/m/v for ADAM, the earlier layers for MEAN, a dense addend).  Both phases
+// are latency bound inside the warp and only overlap ACROSS warps; at 20-25 warps per SM the
+// epilogue's first-touch DRAM loads left the ADAM hop at 66 % DRAM utilisation (ncu r01).  The rows
+// of a chunk are contiguous, so ONE bulk prefetch per operand table, issued while the last
+// entries of the chunk are still being gathered, turns those loads into L2 hits ~1-2 us later
+// (footprint in L2: bandwidth x lead time ~ 10 MB).  Only when the tables stream from HBM (HINT);
+// disabled by LGCN_SPMM_F_NO_PREFETCH.
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
+template <int D, int MODE>
+__device__ __forceinline__ void prefetch_epilogue_rows(const lgcn_spmm_args &a, int64_t r0, int nvr) {
+    if (nvr <= 0 || (a.flags & LGCN_SPMM_F_NO_PREFETCH)) return;
+    const size_t off = (size_t)r0 * D;
+    const uint32_t bytes = (uint32_t)nvr * D * 4;
+    // Measured at the Amazon shape (profiles/r02_prefetch_ab.txt): MEAN 9.27 -> 8.58 ms, dense ADD
+    // 6.30 -> 6.04 ms; ADAM (p, m, v: 24 KB per worker, held for its long epilogue) gains nothing
+    // and loses in the engine's step, and tables narrower than d = 64 lose 4 % -- both excluded.
+    if (D < 64 || MODE == LGCN_SPMM_ADAM) return;
+    if (MODE == LGCN_SPMM_MEAN) {
+        for (int l = 0; l < a.n_layers; ++l) prefetch_l2_bulk(a.layers[l] + off, bytes);
+    } else if (MODE == LGCN_SPMM_ADD) {
+        if (!a.addend_rowflag) prefetch_l2_bulk(a.addend + off, bytes);     // flagged = mostly zero rows
+    }
+}
+
 // ---- epilogue for one row held in registers (long-row combine path) -----------------------
 template <int D, int MODE>
 __device__ __forceinline__ void epilogue_row(const lgcn_spmm_args &a, int64_t row,
@@ -140,13 +168,19 @@ __device__ __forceinline__ void epilogue_row(const lgcn_spmm_args &a, int64_t ro
 }
 
 // ---- chunk epilogue: stream the staged rows, operand loads batched ahead of the math ------
-template <int D, int MODE, int R, bool HINT>
+#ifndef LGCN_MEAN_B4
+#define LGCN_MEAN_B4 4                 // rows per MEAN epilogue batch when at most 4 layers are read
+#endif
+// NLM: compile-time bound of the number of earlier layers the MEAN epilogue reads (8 = the ABI
+// limit; 4 covers K <= 4, i.e. every configuration of the reference: half the operand registers,
+// spent on twice the rows per batch = twice the loads in flight)
+template <int D, int MODE, int R, bool HINT, int NLM = 8>
 __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const float *stage,
                                                int64_t r0, int nvr, unsigned long_bits, uint64_t pol,
                                                const unsigned (&rfw)[R / 4], unsigned wmask = 0xffffffffu) {
     using G = RowGeom<D>;
     const int sub = (threadIdx.x & 31) % G::LANES;
-    constexpr int B = (MODE == LGCN_SPMM_ADAM || MODE == LGCN_SPMM_MEAN) ? 2 : 4;  // rows per batch
+    constexpr int B = MODE == LGCN_SPMM_ADAM ? 2 : (MODE == LGCN_SPMM_MEAN ? (NLM <= 4 ? LGCN_MEAN_B4 : 2) : 4);  // rows per batch
     static_assert(R % B == 0, "chunk rows must be a multiple of the epilogue batch");
     const float div = (float)(a.n_layers + 1);
     float ss = 0.f, bs = 1.f;
@@ -187,18 +221,18 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
                         st_s<HINT>(a.y + off[i], t[i], pol);
                     }
             } else if (MODE == LGCN_SPMM_MEAN) {
-                float4 t[B][8];
+                float4 t[B][NLM];
 #pragma unroll
                 for (int i = 0; i < B; ++i)
 #pragma unroll
-                    for (int l = 0; l < 8; ++l)
+                    for (int l = 0; l < NLM; ++l)
                         if (on[i] && l < a.n_layers) t[i][l] = ld_s<HINT>(a.layers[l] + off[i], pol);
 #pragma unroll
                 for (int i = 0; i < B; ++i)
                     if (on[i]) {
                         float4 s = t[i][0];
 #pragma unroll
-                        for (int l = 1; l < 8; ++l) if (l < a.n_layers) add4(s, t[i][l]);
+                        for (int l = 1; l < NLM; ++l) if (l < a.n_layers) add4(s, t[i][l]);
                         const float4 y = *reinterpret_cast<const float4 *>(stage + (rb + i) * D + coff);
                         add4(s, y);
                         s.x = __fdiv_rn(s.x, div); s.y = __fdiv_rn(s.y, div);
@@ -340,7 +374,12 @@ spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
         for (int v = 0; v < G::VEC; ++v) x[u][v] = zero4;
     }
 
+    bool prefetched = false;
     for (int t = 0; t < max_n; t += G::LANES) {
+        if (HINT && MODE != LGCN_SPMM_PLAIN && !prefetched && t + 2 * G::LANES >= max_n) {   // warp-uniform
+            prefetched = true;
+            if (sub == 0) prefetch_epilogue_rows<D, MODE>(a, r0, nvr);
+        }
         int2 cvn = make_int2(0, 0);
         if (t + G::LANES + sub < n_e) cvn = ld_cv<HINT>(cvp + t + G::LANES + sub, pol);   // next tile, one ahead
         const int cnt = min(n_e - t, G::LANES);           // entries of this tile (may be <= 0)
@@ -415,6 +454,7 @@ spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
         }
         cv = cvn;
     }
+    if (HINT && MODE != LGCN_SPMM_PLAIN && !prefetched && sub == 0) prefetch_epilogue_rows<D, MODE>(a, r0, nvr);
     // rows cur .. nvr-1: the last summed row, then trailing empty rows
     if (cur < nvr) {
 #pragma unroll
@@ -487,7 +527,7 @@ struct RingCfg {
     static_assert(R % 4 == 0, "chunk rows");
 };
 
-template <int D, int MODE, bool HINT>
+template <int D, int MODE, bool HINT, int NLM = 8>
 __global__ void __launch_bounds__(kRingWarps * 32)
 spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
     using G = RowGeom<D>;
@@ -585,7 +625,12 @@ spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
     int cur = 0;                                          // row (within the chunk) being summed
     int cur_end = __shfl_sync(0xffffffffu, my_end, 0, L); // first stream entry past that row
 
+    bool prefetched = false;
     for (int t = 0; t < max_n; t += TL) {                 // cvA = entries [t,t+TL), cvB = [t+TL,t+2TL)
+        if (HINT && MODE != LGCN_SPMM_PLAIN && !prefetched && t + 2 * TL >= max_n) {         // warp-uniform
+            prefetched = true;
+            if (sub == 0) prefetch_epilogue_rows<D, MODE>(a, r0, nvr);
+        }
         bool done = false;
         static_for<TL>([&](auto j_c) {
             constexpr int J = decltype(j_c)::value;
@@ -625,6 +670,7 @@ spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
         cvC = load_tile(t + 3 * TL);
     }
     cp_async_wait<0>();
+    if (HINT && MODE != LGCN_SPMM_PLAIN && !prefetched && sub == 0) prefetch_epilogue_rows<D, MODE>(a, r0, nvr);
     // rows cur .. nvr-1: the last summed row, then trailing empty rows
 #pragma unroll 1
     for (; cur < nvr; ++cur) {
@@ -635,7 +681,7 @@ spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
         }
     }
     __syncwarp();
-    chunk_epilogue<D, MODE, C::R, HINT>(a, stage, r0, nvr, long_bits, pol, rfw);
+    chunk_epilogue<D, MODE, C::R, HINT, NLM>(a, stage, r0, nvr, long_bits, pol, rfw);
 }
 
 // ---- sparse-input hop: live-list kernel --------------------------------------------------------
@@ -963,10 +1009,15 @@ static int launch_live(const lgcn_spmm_args &a, cudaStream_t st) {
 template <int D, int MODE, bool HINT>
 static int launch_ring(const lgcn_spmm_args &a, cudaStream_t st) {
     using C = RingCfg<D>;
-    LGCN_OPT_IN_SMEM((spmm_ring_kernel<D, MODE, HINT>), C::SMEM);
     const int64_t gb = (a.n_rows + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
     if (gb > 0x7fffffffLL) return LGCN_E_TOO_LARGE;
-    spmm_ring_kernel<D, MODE, HINT><<<(unsigned)gb, kRingWarps * 32, C::SMEM, st>>>(a);
+    if (MODE == LGCN_SPMM_MEAN && a.n_layers <= 4) {        // K <= 4: the lean MEAN epilogue
+        LGCN_OPT_IN_SMEM((spmm_ring_kernel<D, MODE, HINT, 4>), C::SMEM);
+        spmm_ring_kernel<D, MODE, HINT, 4><<<(unsigned)gb, kRingWarps * 32, C::SMEM, st>>>(a);
+    } else {
+        LGCN_OPT_IN_SMEM((spmm_ring_kernel<D, MODE, HINT, 8>), C::SMEM);
+        spmm_ring_kernel<D, MODE, HINT, 8><<<(unsigned)gb, kRingWarps * 32, C::SMEM, st>>>(a);
+    }
     LGCN_LAUNCH_CHECK();
     return 0;
 }

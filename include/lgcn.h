@@ -154,6 +154,7 @@ typedef struct lgcn_spmm_args {
 #define LGCN_SPMM_F_BIG_PATH 4      /* large-graph kernels even when the graph is small      */
 #define LGCN_SPMM_F_COLD_FIRST 8    /* gathers of unclassified columns use evict_first too   */
 #define LGCN_SPMM_F_FORCE_RING 16   /* cp.async ring kernel for the ADAM epilogue too        */
+#define LGCN_SPMM_F_NO_PREFETCH 32  /* no L2 prefetch of the epilogue operands (A/B only)    */
 
 #define LGCN_SPMM_PLAIN 0 /* y = A x                                                    */
 #define LGCN_SPMM_ADD   1 /* y = addend + A x              (Horner backward hop)        */
