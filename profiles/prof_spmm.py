@@ -67,6 +67,17 @@ if mode == "addflag":     # a later Horner hop: dense x, addend g' with 3*2048 n
     flag = torch.zeros(N + 32, dtype=torch.uint8, device=dev)
     flag[rows] = 1
     zero_row = torch.zeros(256, device=dev)
+if mode == "hop2":        # second Horner hop: x = first hop's output, ~20 % non-zero rows, flagged; dense out
+    live = torch.rand(N, device=dev) < 0.2
+    x[~live] = 0
+    flag = torch.zeros(N + 32, dtype=torch.uint8, device=dev)
+    flag[:N] = live.to(torch.uint8)
+    rows = torch.randint(0, N, (6144,), device=dev)
+    add = torch.zeros((N, d), device=dev)
+    add[rows] = torch.randn((6144, d), device=dev)
+    aflag = torch.zeros(N + 32, dtype=torch.uint8, device=dev)
+    aflag[rows] = 1
+    zero_row = torch.zeros(256, device=dev)
 if mode in ("hop1", "hop1s"):        # the first Horner hop: x = g' has 3*2048 non-zero rows, flagged
     rows = torch.randint(0, N, (6144,), device=dev)
     x.zero_()
@@ -88,6 +99,8 @@ for i in range(n):
         ops.spmm(g, x, out=y, addend=add, addend_rowflag=flag, zero_row=zero_row)
     elif mode == "hop1":
         ops.spmm(g, x, out=y, addend=add, x_rowflag=flag, addend_rowflag=flag, zero_row=zero_row)
+    elif mode == "hop2":
+        ops.spmm(g, x, out=y, addend=add, x_rowflag=flag, addend_rowflag=aflag, zero_row=zero_row)
     elif mode == "hop1s":     # + sparse output (all-zero rows not written, reported in yflag)
         ops.spmm(g, x, out=y, addend=add, x_rowflag=flag, addend_rowflag=flag, zero_row=zero_row,
                  y_rowflag=yflag)
