@@ -319,6 +319,11 @@ def run_b200(args):
     if world > 1 and args.parallelism == "row":
         extra.update(add=1, adam=7)                  # the row-sharded engine reads its addends densely
     kernels = {}
+    other = {}                       # non-SpMM launches of the step (fusion projection, standalone Adam)
+    for tag in [t for t in per_tag if t not in extra]:
+        v = per_tag.pop(tag)
+        other[tag] = {"launches": len(v), "avg_ms": float(np.mean(v)),
+                      "ms_per_step": float(np.sum(v)) / max(args.steps, 1)}
     for tag, v in per_tag.items():
         ms = float(np.mean(v))
         by = _spmm_bytes(g_local.n_rows, g_local.nnz, d_local, extra[tag])
@@ -446,7 +451,7 @@ def run_b200(args):
             "e2e": {"value": e2e_ms * steps_per_epoch / 1e3, "unit": "s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 3 * BS * 8, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
-            "roofline": roofline, "kernels": kernels, "eval": ev, "cpu_baseline": cpu,
+            "roofline": roofline, "kernels": kernels, "other_kernels": other, "eval": ev, "cpu_baseline": cpu,
             "loss": last_loss, "witness": witness,
         }
         os.write(out_fd, (json.dumps(line) + "\n").encode())

@@ -22,8 +22,10 @@ SPMM_F_BIG_PATH = 4
 SPMM_F_COLD_FIRST = 8
 SPMM_F_FORCE_RING = 16
 SPMM_F_NO_PREFETCH = 32
+SPMM_F_ALT_X = 64
+SPMM_F_ALT_LAYER0 = 128
 BPR_GP_INCLUDES_GF, BPR_NO_GRAD = 1, 2
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class SpmmArgs(ctypes.Structure):
@@ -38,6 +40,8 @@ class SpmmArgs(ctypes.Structure):
         ("beta1", c_f32), ("beta2", c_f32), ("eps", c_f32), ("g_out", c_vp),
         ("flags", c_i32), ("x_rowflag", c_vp), ("addend_rowflag", c_vp), ("zero_row", c_vp),
         ("y_rowflag", c_vp),
+        ("x_alt", c_vp), ("alt_begin", c_i64), ("alt_rows", c_i64),
+        ("g_skip", c_vp), ("skip_begin", c_i64), ("skip_rows", c_i64),
     ]
 
 

@@ -98,6 +98,27 @@ __device__ __forceinline__ uint64_t pick_policy(const GatherPolicy &g, int col_r
     return col_raw < 0 ? g.last : ((col_raw & LGCN_COL_ONCE) ? g.first : g.mid);
 }
 
+// ---- layer-0 override / ADAM row skip (lgcn_spmm_args.x_alt, g_skip) --------------------------
+// Both ranges are tested with one unsigned compare; the alternative base pointer is pre-shifted by
+// the range start so that the SAME row index addresses either table.
+struct AltRange {
+    uint32_t lo, n;                 // rows [lo, lo + n); n == 0: never taken
+    __device__ __forceinline__ bool has(int r) const { return (uint32_t)r - lo < n; }
+};
+__device__ __forceinline__ AltRange alt_x_range(const lgcn_spmm_args &a) {
+    return AltRange{(uint32_t)a.alt_begin, (a.flags & LGCN_SPMM_F_ALT_X) ? (uint32_t)a.alt_rows : 0u};
+}
+__device__ __forceinline__ AltRange alt_layer0_range(const lgcn_spmm_args &a) {
+    return AltRange{(uint32_t)a.alt_begin, (a.flags & LGCN_SPMM_F_ALT_LAYER0) ? (uint32_t)a.alt_rows : 0u};
+}
+__device__ __forceinline__ AltRange adam_skip_range(const lgcn_spmm_args &a) {
+    return AltRange{(uint32_t)a.skip_begin, a.g_skip ? (uint32_t)a.skip_rows : 0u};
+}
+template <int D>
+__device__ __forceinline__ const float *alt_shifted(const lgcn_spmm_args &a) {      // x_alt - alt_begin rows
+    return a.x_alt ? a.x_alt - (size_t)a.alt_begin * D : a.x;
+}
+
 // ---- L2 prefetch of the epilogue's operand rows ---------------------------------------------
 // A worker first walks its chunk's entries (gather phase), then streams the chunk's rows of the
 // epilogue operands (p/m/v for ADAM, the earlier layers for MEAN, a dense addend).  Both phases
@@ -142,7 +163,8 @@ __device__ __forceinline__ void epilogue_row(const lgcn_spmm_args &a, int64_t ro
             add4(g, acc[v]);
             st_f4(a.y + off, g);
         } else if (MODE == LGCN_SPMM_MEAN) {
-            float4 s = ld_stream_f4(a.layers[0] + off);
+            const float *l0 = alt_layer0_range(a).has((int)row) ? alt_shifted<D>(a) : a.layers[0];
+            float4 s = ld_stream_f4(l0 + off);
             for (int l = 1; l < a.n_layers; ++l) {
                 const float4 t = ld_stream_f4(a.layers[l] + off);
                 add4(s, t);
@@ -155,6 +177,10 @@ __device__ __forceinline__ void epilogue_row(const lgcn_spmm_args &a, int64_t ro
         } else {  // LGCN_SPMM_ADAM
             float4 g = acc[v];
             if (a.addend) { const float4 t = ld_stream_f4(a.addend + off); add4(g, t); }
+            if (adam_skip_range(a).has((int)row)) {      // not a parameter row: hand the gradient on
+                st_f4(a.g_skip - (size_t)a.skip_begin * D + off, g);
+                continue;
+            }
             if (a.addend2) { const float4 t = ld_stream_f4(a.addend2 + off); add4(g, t); }
             float4 p = *reinterpret_cast<const float4 *>(a.p + off);
             float4 m = *reinterpret_cast<const float4 *>(a.m + off);
@@ -180,7 +206,10 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
                                                const unsigned (&rfw)[R / 4], unsigned wmask = 0xffffffffu) {
     using G = RowGeom<D>;
     const int sub = (threadIdx.x & 31) % G::LANES;
-    constexpr int B = MODE == LGCN_SPMM_ADAM ? 2 : (MODE == LGCN_SPMM_MEAN ? (NLM <= 4 ? LGCN_MEAN_B4 : 2) : 4);  // rows per batch
+    // rows per batch.  ADAM: 2 rows of g / g2 / p / m / v are 40 operand registers; 4 rows lose 23 % at
+    // d = 128 (14.18 vs 11.49 ms) but win 7 % at d = 16 (2.27 vs 2.44 ms); d = 32 loses again (4.55 vs 3.45 ms)
+    constexpr int B = MODE == LGCN_SPMM_ADAM ? ((D <= 16 && R % 4 == 0) ? 4 : 2)
+                                              : (MODE == LGCN_SPMM_MEAN ? (NLM <= 4 ? LGCN_MEAN_B4 : 2) : 4);
     static_assert(R % B == 0, "chunk rows must be a multiple of the epilogue batch");
     const float div = (float)(a.n_layers + 1);
     float ss = 0.f, bs = 1.f;
@@ -197,6 +226,7 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
                 on[i] = rr < nvr && !((long_bits >> rr) & 1u) && ((wmask >> rr) & 1u);
                 off[i] = (size_t)(r0 + rr) * D + coff;
             }
+            [[maybe_unused]] const AltRange alt0 = alt_layer0_range(a), skip = adam_skip_range(a);
             if (MODE == LGCN_SPMM_PLAIN) {
 #pragma unroll
                 for (int i = 0; i < B; ++i)
@@ -226,7 +256,10 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
                 for (int i = 0; i < B; ++i)
 #pragma unroll
                     for (int l = 0; l < NLM; ++l)
-                        if (on[i] && l < a.n_layers) t[i][l] = ld_s<HINT>(a.layers[l] + off[i], pol);
+                        if (on[i] && l < a.n_layers) {
+                            const float *lp = (l == 0 && alt0.has((int)(r0 + rb + i))) ? alt_shifted<D>(a) : a.layers[l];
+                            t[i][l] = ld_s<HINT>(lp + off[i], pol);
+                        }
 #pragma unroll
                 for (int i = 0; i < B; ++i)
                     if (on[i]) {
@@ -241,22 +274,30 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
                     }
             } else {  // ADAM
                 float4 g[B], p[B], m[B], vv[B], g2[B];
+                bool sk[B];
 #pragma unroll
-                for (int i = 0; i < B; ++i)
+                for (int i = 0; i < B; ++i) {
+                    sk[i] = skip.has((int)(r0 + rb + i));
                     if (on[i]) {
                         const bool nz = ((rfw[(rb + i) >> 2] >> (((rb + i) & 3) * 8)) & 0xffu) != 0;
                         g[i] = g2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (a.addend && nz) g[i] = ld_s<HINT>(a.addend + off[i], pol);
+                        if (sk[i]) continue;               // not a parameter row: no p / m / v traffic
                         if (a.addend2 && nz) g2[i] = ld_s<HINT>(a.addend2 + off[i], pol);
                         p[i] = ld_s<HINT>(a.p + off[i], pol);
                         m[i] = ld_s<HINT>(a.m + off[i], pol);
                         vv[i] = ld_s<HINT>(a.v + off[i], pol);
                     }
+                }
 #pragma unroll
                 for (int i = 0; i < B; ++i)
                     if (on[i]) {
                         float4 gr = *reinterpret_cast<const float4 *>(stage + (rb + i) * D + coff);
                         if (a.addend) add4(gr, g[i]);
+                        if (sk[i]) {                       // hand the gradient to the projection's backward
+                            st_s<HINT>(a.g_skip - (size_t)a.skip_begin * D + off[i], gr, pol);
+                            continue;
+                        }
                         if (a.addend2) add4(gr, g2[i]);
                         adam4(p[i], m[i], vv[i], gr, ss, bs, a.beta1, a.beta2, a.eps);
                         st_s<HINT>(a.p + off[i], p[i], pol);
@@ -352,6 +393,8 @@ spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
     const int2 *cvp = reinterpret_cast<const int2 *>(a.colval) + chunk_beg;
     int2 cv = make_int2(0, 0);
     if (sub < n_e) cv = ld_cv<HINT>(cvp + sub, pol);
+    [[maybe_unused]] const AltRange altx = alt_x_range(a);
+    [[maybe_unused]] const float *xalt = alt_shifted<D>(a);
 
     float4 acc[G::VEC];
 #pragma unroll
@@ -415,7 +458,8 @@ spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int cr = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
-                    const float *src = a.x + (size_t)(cr & LGCN_COL_MASK) * D + sub * 4;
+                    const int cc = cr & LGCN_COL_MASK;
+                    const float *src = (altx.has(cc) ? xalt : a.x) + (size_t)cc * D + sub * 4;
                     if (HINT) {
                         const uint64_t gp = pick_policy(gpol, cr);
 #pragma unroll
@@ -580,6 +624,8 @@ spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
         max_n = max(max_n, __shfl_xor_sync(0xffffffffu, max_n, off));
 
     const char *xb = reinterpret_cast<const char *>(a.x + sub * 4);
+    const char *xab = reinterpret_cast<const char *>(alt_shifted<D>(a) + sub * 4);
+    const AltRange altx = alt_x_range(a);
     const int2 *cvp = reinterpret_cast<const int2 *>(a.colval) + chunk_beg;
     const int2 z2 = make_int2(0, 0);
     // {col,val} tiles of TL stream entries: lane `sub` holds entries sub*EPL .. sub*EPL+EPL-1
@@ -603,7 +649,8 @@ spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
         constexpr int JT = JJ % TL;
         const int cr = __shfl_sync(0xffffffffu, JJ < TL ? cvA.e[JT % EPL].x : cvB.e[JT % EPL].x, JT / EPL, L);
         if (t + JJ < n_e) {
-            const char *src = xb + (uint64_t)(uint32_t)(cr & LGCN_COL_MASK) * (D * 4);
+            const int cc = cr & LGCN_COL_MASK;
+            const char *src = (altx.has(cc) ? xab : xb) + (uint64_t)(uint32_t)cc * (D * 4);
             const uint32_t dst = ring_s + (uint32_t)(JJ % S) * (D * 4);
             if (GHINT) {
                 const uint64_t gp = pick_policy(gpol, cr);
@@ -861,6 +908,8 @@ __device__ __forceinline__ void long_seg_body(const lgcn_spmm_args &a, int64_t b
 #pragma unroll
     for (int v = 0; v < G::VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int2 *cvp = reinterpret_cast<const int2 *>(a.long_colval) + beg;
+    const AltRange altx = alt_x_range(a);
+    const float *xalt = alt_shifted<D>(a);
     if (a.x_rowflag) {
         // flagged input (the sparse backward hops): one flag byte per lane for the whole tile, a
         // ballot of the live entries, and only those are gathered and summed -- in stream order,
@@ -916,7 +965,7 @@ __device__ __forceinline__ void long_seg_body(const lgcn_spmm_args &a, int64_t b
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
                 const int cj = __shfl_sync(0xffffffffu, cv.x, j + u, G::LANES);
-                const float *src = a.x + (size_t)cj * D + sub * 4;
+                const float *src = (altx.has(cj) ? xalt : a.x) + (size_t)cj * D + sub * 4;
 #pragma unroll
                 for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
             }
@@ -1030,11 +1079,14 @@ static bool small_graph(int64_t n_rows, int32_t flags) {
     return big_workers < (int64_t)kNumSMs * 32 * RowGeom<D>::GROUPS && !(flags & LGCN_SPMM_F_BIG_PATH);
 }
 
-// Large graphs: the cp.async ring kernel; the flagged (sparse-input) hops run the live-list
-// kernel.  ADAM (its epilogue wants the registers) keeps the register-batch chunk kernel.
+// Large graphs: the cp.async ring kernel for every epilogue; the flagged (sparse-input) hops run
+// the live-list kernel.  (Round 1 kept the register-batch chunk kernel for ADAM; re-measured in
+// round 2 the ring kernel wins at every width: d=16 2.95 -> 2.44 ms, d=32 4.34 -> 3.45, d=64
+// 6.77 -> 5.74, d=128 12.18 -> 11.49 -- profiles/r02_adam_ring.txt.  LGCN_SPMM_F_NO_RING still
+// selects the chunk kernel; LGCN_SPMM_F_FORCE_RING is kept for ABI compatibility and is a no-op.)
 static bool ring_path(bool small, int mode, int32_t flags) {
-    return !small && !(flags & LGCN_SPMM_F_NO_RING) &&
-           (mode != LGCN_SPMM_ADAM || (flags & LGCN_SPMM_F_FORCE_RING));
+    (void)mode;
+    return !small && !(flags & LGCN_SPMM_F_NO_RING);
 }
 
 template <int D, int MODE>
@@ -1110,6 +1162,15 @@ extern "C" int lgcn_spmm(const lgcn_spmm_args *args, lgcn_stream_t stream) {
     if ((a.x_rowflag || a.addend_rowflag) && !a.zero_row) return LGCN_E_BAD_ARG;
     if (a.x_rowflag && a.mode != LGCN_SPMM_ADD) return LGCN_E_BAD_ARG;
     if (a.y_rowflag && !(a.x_rowflag && a.addend_rowflag)) return LGCN_E_BAD_ARG;
+    if (a.flags & (LGCN_SPMM_F_ALT_X | LGCN_SPMM_F_ALT_LAYER0)) {
+        if (!a.x_alt || a.alt_begin < 0 || a.alt_rows < 0 || a.alt_begin + a.alt_rows > 0x7fffffffLL)
+            return LGCN_E_BAD_ARG;
+        if ((a.flags & LGCN_SPMM_F_ALT_X) && a.x_rowflag) return LGCN_E_BAD_ARG;
+        if ((a.flags & LGCN_SPMM_F_ALT_LAYER0) && a.mode != LGCN_SPMM_MEAN) return LGCN_E_BAD_ARG;
+    }
+    if (a.g_skip && (a.mode != LGCN_SPMM_ADAM || a.skip_begin < 0 || a.skip_rows < 0 ||
+                     a.skip_begin + a.skip_rows > a.n_rows))
+        return LGCN_E_BAD_ARG;
     if (a.n_long > 0 && (!a.long_row_ids || !a.long_rowptr || !a.long_colval || !a.long_seg_ptr ||
                          !a.seg_ws || a.seg_len <= 0 || a.n_seg <= 0))
         return LGCN_E_BAD_ARG;

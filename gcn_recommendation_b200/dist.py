@@ -95,7 +95,7 @@ class FeatureShardedEngine(LightGCNEngine):
         new = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=self.dev)  # noqa: E731
         self.fusion = dict(C=C.contiguous(), W=W, b=b, mW=z(W), vW=z(W), mb=z(b), vb=z(b),
                            gW=z(W), gb=z(b), g_eid=new(self.I, self.d))
-        self.X0 = new(self.N, self.d)
+        self.H, self.gH = new(self.I, self.d), new(self.I, self.d)     # column shards of H and dL/dH
         self.a2a_in, self.a2a_out = new(P_, self.ipr, self.d), new(P_, self.ipr, self.d)
         self.E_rows, self.H_rows = new(self.ipr, self.d_full), new(self.ipr, self.d_full)
         self.G_rows, self.GE_rows = new(self.ipr, self.d_full), new(self.ipr, self.d_full)
@@ -115,21 +115,19 @@ class FeatureShardedEngine(LightGCNEngine):
 
     def layer0(self):
         if self.fusion is None:
-            return self.P
+            return self.P, None
         U, I, f, n = self.U, self.I, self.fusion, self.i_loc
-        self.X0[:U].copy_(self.P[:U])
-        self.X0[U + I:].copy_(self.P[U + I:])
         self._cols_to_rows(self.P[U:U + I], self.E_rows)
         if n > 0:
             ops.fusion_proj_fwd(self.E_rows[:n], f["C"], f["W"], f["b"], out=self.H_rows[:n])
-        self._rows_to_cols(self.H_rows, self.X0[U:U + I])
-        return self.X0
+        self._rows_to_cols(self.H_rows, self.H)
+        return self.P, (self.H, U)
 
-    def _fusion_backward(self, acc):
+    def _fusion_backward(self, gH):
         U, I, f, n = self.U, self.I, self.fusion, self.i_loc
         f["gW"].zero_()
         f["gb"].zero_()
-        self._cols_to_rows(acc[U:U + I], self.G_rows)               # dL/dH rows of the item block
+        self._cols_to_rows(gH, self.G_rows)                          # dL/dH rows of the item block
         if n > 0:                                                    # E_rows / H_rows: kept from layer0
             ops.fusion_proj_bwd(self.E_rows[:n], f["C"], f["W"], self.H_rows[:n], self.G_rows[:n],
                                 g_eid=self.GE_rows[:n], gW=f["gW"], gb=f["gb"])

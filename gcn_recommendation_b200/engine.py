@@ -106,9 +106,9 @@ class LightGCNEngine:
         self.m = torch.zeros_like(self.P)
         self.v = torch.zeros_like(self.P)
         self.F = new()
-        # E_1..E_{K-1}, reused as the Horner ping-pong; K == 1 with the fusion block still runs one
-        # backward hop, which must not land in F (rate_topk(propagate=False) reads F afterwards)
-        self.work = [new() for _ in range(max(self.K - 1, 2 if self.K > 1 else (1 if fusion is not None else 0)))]
+        # E_1..E_{K-1}, reused as the Horner ping-pong of the K-1 ADD hops (never F: a later
+        # rate_topk(propagate=False) reads F)
+        self.work = [new() for _ in range(max(self.K - 1, 2 if self.K > 1 else 0))]
         self.G1 = torch.zeros_like(self.P)          # g/(K+1): addend of every Horner hop
         self.G2 = torch.zeros_like(self.P)          # regulariser grad (+ g/(K+1) w/o fusion)
         # 1 = row received a gradient this step (G1/G2 are zero elsewhere): lets the backward
@@ -170,7 +170,11 @@ class LightGCNEngine:
         self.fusion = dict(C=C.contiguous(), W=W, b=b, mW=z(W), vW=z(W), mb=z(b), vb=z(b),
                            gW=z(W), gb=z(b),
                            g_eid=torch.empty((self.I, self.d), dtype=torch.float32, device=self.dev))
-        self.X0 = torch.empty((self.N, self.d), dtype=torch.float32, device=self.dev)
+        # projected item rows H (layer 0 = the parameter table with its item rows overridden by H:
+        # lgcn_spmm's x_alt, so the concatenated table of reference lightgcn_fusion.py:52 is never
+        # built) and dL/dH, written by the ADAM hop for the rows it skips
+        self.H = torch.empty((self.I, self.d), dtype=torch.float32, device=self.dev)
+        self.gH = torch.empty((self.I, self.d), dtype=torch.float32, device=self.dev)
 
     def _count_launches(self):
         """Kernels of THIS library launched per training step (for bench.py's gpu_launches)."""
@@ -179,36 +183,37 @@ class LightGCNEngine:
         if self.brand_w != 0.0:
             n += 2 + 1                                 # brand term (+reduce), its zero_rows
         if self.fusion is not None:
-            n += 1 + 2 + 5                             # proj fwd, proj bwd (2), 5 adam launches
+            n += 1 + 2 + 3                             # proj fwd, proj bwd (2), Adam of item ids / W / b
         return n
 
     # ---- pieces ----------------------------------------------------------------------------
     def layer0(self):
-        """Input of the propagation: the table itself, or with the fused item block."""
+        """Input of the propagation as (table, alt): the parameter table itself, and with the
+        fusion block ``alt = (H, U)`` -- its item rows are the projected rows H (reference
+        ``models/lightgcn_fusion.py:45-52``), read in place of the raw id rows by the kernels."""
         if self.fusion is None:
-            return self.P
+            return self.P, None
         U, I = self.U, self.I
         f = self.fusion
-        self.X0[:U].copy_(self.P[:U])
-        self.X0[U + I:].copy_(self.P[U + I:])
-        ops.fusion_proj_fwd(self.P[U:U + I], f["C"], f["W"], f["b"], out=self.X0[U:U + I])
-        return self.X0
+        ops.fusion_proj_fwd(self.P[U:U + I], f["C"], f["W"], f["b"], out=self.H)
+        return self.P, (self.H, U)
 
-    def _fusion_backward(self, acc):
-        """Gradients of the fused item block from dL/dX0 (``acc``): fills ``g_eid`` (id
+    def _fusion_backward(self, gH):
+        """Gradients of the fused item block from dL/dH (``gH`` [I, d]): fills ``g_eid`` (id
         embeddings), ``gW`` and ``gb`` (autograd of reference ``models/lightgcn_fusion.py:45-49``)."""
         U, I = self.U, self.I
         f = self.fusion
         f["gW"].zero_()
         f["gb"].zero_()
-        ops.fusion_proj_bwd(self.P[U:U + I], f["C"], f["W"], self.X0[U:U + I], acc[U:U + I],
+        ops.fusion_proj_bwd(self.P[U:U + I], f["C"], f["W"], self.H, gH,
                             g_eid=f["g_eid"], gW=f["gW"], gb=f["gb"])
 
     def propagate(self):
         """F = mean_k A^k E0 (reference ``models/lightgcn.py:44-54``); returns the [N,d] table."""
         if self._tc is not None:
             self._tc.prepared_for = None            # the bf16 item tiles belong to the old table
-        return ops.propagate(self.g, self.layer0(), self.K, out=self.F, work=self.work)
+        x, alt = self.layer0()
+        return ops.propagate(self.g, x, self.K, out=self.F, work=self.work, alt=alt)
 
     def forward(self):
         """The reference's 5-tuple (``models/lightgcn.py:81``) as views, no autograd."""
@@ -246,31 +251,32 @@ class LightGCNEngine:
         self._bpr(F, nofus)
         ops.adam_tick(self.step_dev, self.adam_scalars, self.lr, self.betas)
         acc = self.G1
-        hops = K - 1 if nofus else K
         rf, zr = self.rowflag, self.zero_row
-        rf2 = self.rowflag2 if (self.sparse_hops and hops >= 2) else None
-        for k in range(hops):
+        rf2 = self.rowflag2 if (self.sparse_hops and K - 1 >= 2) else None
+        for k in range(K - 1):
             # hop 0 gathers g' itself (<= 3*batch non-zero rows): flagged gathers, and only the
             # rows next to the batch's nodes are written (flags in rf2); hop 1 gathers under rf2
             # (still ~80 % zero rows at the Amazon shape).  The addend of every hop is g' too: its
             # all-zero rows are not read (1 ms per hop at the Amazon shape)
-            acc = ops.spmm(g, acc, out=self.work[k % 2] if K > 1 else self.work[0], addend=self.G1,
+            acc = ops.spmm(g, acc, out=self.work[k % 2], addend=self.G1,
                            x_rowflag=rf if k == 0 else (rf2 if k == 1 else None), addend_rowflag=rf,
                            zero_row=zr, y_rowflag=rf2 if k == 0 else None)
         if nofus:
             ops.spmm_adam(g, acc, self.P, self.m, self.v, self.adam_scalars, addend=self.G2,
                           betas=self.betas, eps=self.eps, addend_rowflag=rf, zero_row=zr)
         else:
+            # the K-th hop updates the user / brand rows (grad = g' + A acc + reg) and hands
+            # dL/dH = g' + A acc of the item rows to the projection's backward; the item-id rows,
+            # W and b then take their own (small) Adam launches
             f = self.fusion
-            self._fusion_backward(acc)
+            ops.spmm_adam(g, acc, self.P, self.m, self.v, self.adam_scalars, addend=self.G1,
+                          addend2=self.G2, betas=self.betas, eps=self.eps, addend_rowflag=rf,
+                          zero_row=zr, skip=(self.gH, U))
+            self._fusion_backward(self.gH)
             kw = dict(betas=self.betas, eps=self.eps)
             sc = self.adam_scalars
-            ops.adam(self.P[:U], acc[:U], self.m[:U], self.v[:U], sc, g1=self.G2[:U], **kw)
             ops.adam(self.P[U:U + I], f["g_eid"], self.m[U:U + I], self.v[U:U + I], sc,
                      g1=self.G2[U:U + I], **kw)
-            if self.B > 0:
-                ops.adam(self.P[U + I:], acc[U + I:], self.m[U + I:], self.v[U + I:], sc,
-                         g1=self.G2[U + I:], **kw)
             ops.adam(f["W"], f["gW"], f["mW"], f["vW"], sc, **kw)
             ops.adam(f["b"], f["gb"], f["mb"], f["vb"], sc, **kw)
         ops.zero_rows(self.G1, self.G2, u, p, n, U, rowflag=self.rowflag)

@@ -53,6 +53,24 @@ def on_device(fn):
     return wrapped
 
 
+class _timed:
+    """``with _timed(tag):`` -- CUDA events around a launch when bench.py collects a PROFILE."""
+
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.s, self.e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.s.record()
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e.record()
+            PROFILE.append((self.tag, self.s, self.e))
+        return False
+
+
 def _spmm_plan(n_rows, d, n_long):
     """(kernel launches per ``lgcn_spmm`` call, small-graph path?) as the library itself decides
     (host-only query, csrc/lgcn_spmm.cu ``launch_mode``)."""
@@ -127,16 +145,32 @@ def _check_table(t, rows, d, name):
         raise _lib.LgcnError(f"{name}: expected at least [{rows},{d}], got {tuple(t.shape)}")
 
 
+def _set_alt(a, alt, d, gather, layer0):
+    """Layer-0 override: ``alt = (rows [n, d], first_row)`` -- those rows of the gathered table
+    (``gather``) and / or of ``layers[0]`` (``layer0``) are read from ``rows`` instead."""
+    rows, begin = alt
+    if rows.dim() != 2 or rows.shape[1] != d:
+        raise _lib.LgcnError("x_alt: expected [rows, d]")
+    a.x_alt = ptr(rows)
+    a.alt_begin, a.alt_rows = int(begin), int(rows.shape[0])
+    a.flags |= (_lib.SPMM_F_ALT_X if gather else 0) | (_lib.SPMM_F_ALT_LAYER0 if layer0 else 0)
+
+
 @on_device
 def spmm(g, x, out=None, addend=None, mean_layers=None, x_rowflag=None, addend_rowflag=None,
-         zero_row=None, y_rowflag=None):
+         zero_row=None, y_rowflag=None, x_alt=None, layer0_alt=None):
     """out = A_hat x  (+ addend)  |  mean over [*mean_layers, A_hat x] (reference
     ``models/lightgcn.py:45,54``).  ``g``: :class:`graph.NormAdjCSR`; ``x`` [n_cols, d].
 
     Sparse-gradient shortcuts of the backward hops (include/lgcn.h): ``x_rowflag`` /
     ``addend_rowflag`` mark the non-zero rows of ``x`` / ``addend``; with ``y_rowflag`` the kernel
     reports which output rows can be non-zero and leaves the others UNWRITTEN (pass it as the
-    next hop's ``x_rowflag``)."""
+    next hop's ``x_rowflag``).
+
+    ``x_alt = (rows, first_row)``: the LightGCN_Fusion layer 0 -- rows ``[first_row, first_row +
+    len(rows))`` of ``x`` are gathered from ``rows`` instead (the projected item block), so the
+    concatenated layer-0 table of reference ``models/lightgcn_fusion.py:52`` is never built;
+    ``layer0_alt``: the same override for ``mean_layers[0]``."""
     d = x.shape[1]
     _check_table(x, g.n_cols, d, "x")
     if out is None:
@@ -166,6 +200,13 @@ def spmm(g, x, out=None, addend=None, mean_layers=None, x_rowflag=None, addend_r
                 a.y_rowflag = ptr(y_rowflag, "u8")
     else:
         a = _spmm_args(g, x, SPMM_PLAIN, d)
+    if x_alt is not None or layer0_alt is not None:
+        if x_alt is not None and layer0_alt is not None and x_alt[0].data_ptr() != layer0_alt[0].data_ptr():
+            raise _lib.LgcnError("x_alt and layer0_alt must be the same rows")
+        if x_rowflag is not None:
+            raise _lib.LgcnError("x_alt cannot be combined with x_rowflag")
+        _set_alt(a, x_alt if x_alt is not None else layer0_alt, d, x_alt is not None,
+                 layer0_alt is not None and mean_layers is not None)
     a.y = ptr(out)
     tag = ("plain", "add", "mean")[a.mode]
     if x_rowflag is not None:
@@ -176,9 +217,11 @@ def spmm(g, x, out=None, addend=None, mean_layers=None, x_rowflag=None, addend_r
 
 @on_device
 def spmm_adam(g, x, p, m, v, adam_scalars, addend=None, addend2=None, betas=(0.9, 0.999),
-              eps=1e-8, g_out=None, addend_rowflag=None, zero_row=None):
+              eps=1e-8, g_out=None, addend_rowflag=None, zero_row=None, skip=None):
     """Last backward hop fused with Adam: grad = addend + A_hat x + addend2; Adam(p, m, v, grad)
-    (reference ``main.py:525-526``)."""
+    (reference ``main.py:525-526``).  ``skip = (g_rows [n, d], first_row)``: those rows are not
+    parameters of this table (LightGCN_Fusion item rows: produced by the projection) -- they are
+    left alone and their gradient ``addend + A_hat x`` is written to ``g_rows``."""
     d = x.shape[1]
     a = _spmm_args(g, x, SPMM_ADAM, d)
     for t, n in ((p, "p"), (m, "m"), (v, "v")):
@@ -192,20 +235,28 @@ def spmm_adam(g, x, p, m, v, adam_scalars, addend=None, addend2=None, betas=(0.9
     if addend_rowflag is not None:
         a.addend_rowflag = ptr(addend_rowflag, "u8")
         a.zero_row = ptr(zero_row)
+    if skip is not None:
+        rows, begin = skip
+        if rows.dim() != 2 or rows.shape[1] != d or begin < 0 or begin + rows.shape[0] > g.n_rows:
+            raise _lib.LgcnError("skip: expected ([rows, d], first_row) inside the table")
+        a.g_skip = ptr(rows)
+        a.skip_begin, a.skip_rows = int(begin), int(rows.shape[0])
     _launch_spmm(a, g, x.device, "adam")
 
 
-def propagate(g, e0, n_layers, out=None, work=None):
+def propagate(g, e0, n_layers, out=None, work=None, alt=None):
     """K-layer propagation with the layer mean fused into the last SpMM (reference
     ``models/lightgcn.py:44-54``).  Returns F [N,d].  ``work``: optional list of K-1 scratch
-    tables (E_1..E_{K-1})."""
+    tables (E_1..E_{K-1}).  ``alt = (rows, first_row)``: layer 0 is ``e0`` with those rows
+    replaced (LightGCN_Fusion's projected item block) without materialising it."""
     if n_layers < 1:
         raise _lib.LgcnError("n_layers must be >= 1")
     layers = [e0]
     for k in range(n_layers - 1):
         buf = work[k] if work is not None else None
-        layers.append(spmm(g, layers[-1], out=buf))
-    return spmm(g, layers[-1], out=out, mean_layers=layers)
+        layers.append(spmm(g, layers[-1], out=buf, x_alt=alt if k == 0 else None))
+    return spmm(g, layers[-1], out=out, mean_layers=layers, x_alt=alt if n_layers == 1 else None,
+                layer0_alt=alt)
 
 
 def propagate_backward(g, grad_f, n_layers, work=None):
@@ -323,9 +374,10 @@ def adam_tick(step_dev, scalars, lr, betas=(0.9, 0.999)):
 @on_device
 def adam(p, g0, m, v, scalars, g1=None, betas=(0.9, 0.999), eps=1e-8):
     COUNTERS["launches"] += 1
-    check(_lib.load().lgcn_adam(ptr(p), ptr(g0), ptr(g1, allow_none=True), ptr(m), ptr(v),
-                                p.numel(), ptr(scalars), betas[0], betas[1], eps,
-                                stream_ptr(p.device)))
+    with _timed("adam_standalone"):
+        check(_lib.load().lgcn_adam(ptr(p), ptr(g0), ptr(g1, allow_none=True), ptr(m), ptr(v),
+                                    p.numel(), ptr(scalars), betas[0], betas[1], eps,
+                                    stream_ptr(p.device)))
 
 
 @on_device
@@ -339,8 +391,9 @@ def fusion_proj_fwd(e_id, content, W, b, out=None):
     if out is None:
         out = torch.empty((n, d), dtype=torch.float32, device=e_id.device)
     COUNTERS["launches"] += 1
-    check(_lib.load().lgcn_fusion_proj_fwd(ptr(e_id), ptr(content), ptr(W), ptr(b), n, d, c,
-                                           ptr(out), stream_ptr(e_id.device)))
+    with _timed("fusion_fwd"):
+        check(_lib.load().lgcn_fusion_proj_fwd(ptr(e_id), ptr(content), ptr(W), ptr(b), n, d, c,
+                                               ptr(out), stream_ptr(e_id.device)))
     return out
 
 
@@ -356,8 +409,9 @@ def fusion_proj_bwd(e_id, content, W, H, gH, g_eid=None, gW=None, gb=None):
     if gb is None:
         gb = torch.zeros((d,), dtype=torch.float32, device=dev)
     COUNTERS["launches"] += 2
-    check(_lib.load().lgcn_fusion_proj_bwd(ptr(e_id), ptr(content), ptr(W), ptr(H), ptr(gH), n, d,
-                                           c, ptr(g_eid), ptr(gW), ptr(gb), stream_ptr(dev)))
+    with _timed("fusion_bwd"):
+        check(_lib.load().lgcn_fusion_proj_bwd(ptr(e_id), ptr(content), ptr(W), ptr(H), ptr(gH), n, d,
+                                               c, ptr(g_eid), ptr(gW), ptr(gb), stream_ptr(dev)))
     return g_eid, gW, gb
 
 
@@ -518,10 +572,10 @@ class PropagateFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, g, n_layers, *tables):
-        e0 = _as_block(tables)
+        e0, alt = _as_block(tables)
         ctx.g, ctx.n_layers = g, n_layers
         ctx.sizes = [t.shape[0] for t in tables]
-        return propagate(g, e0, n_layers)
+        return propagate(g, e0, n_layers, alt=alt)
 
     @staticmethod
     def backward(ctx, grad_f):
@@ -534,22 +588,38 @@ class PropagateFunction(torch.autograd.Function):
 
 
 def _as_block(tables):
-    """Zero-copy [N,d] view when the tables are consecutive slices of one allocation
-    (models/_packing.py arranges that), else one concat (reference ``lightgcn.py:40``)."""
+    """(block [N,d], alt): a zero-copy view when the tables are consecutive slices of one
+    allocation (models/_packing.py arranges that).  LightGCN_Fusion hands (users, PROJECTED items,
+    brands): users and brands still sit in the packed block around the raw item-id rows, so the
+    block is used as layer 0 with the projected rows as its override ``alt = (rows, first_row)``
+    -- no concat (reference ``lightgcn_fusion.py:52`` builds one every forward).  Anything else is
+    concatenated like the reference does (``lightgcn.py:40``)."""
     t0 = tables[0]
     d = t0.shape[1]
     ok = all(t.is_contiguous() and t.shape[1] == d and t.dtype == torch.float32 for t in tables)
+    n = sum(t.shape[0] for t in tables)
+
+    def same_storage(t):
+        return t.untyped_storage().data_ptr() == t0.untyped_storage().data_ptr()
+
     if ok:
         end = t0.data_ptr()
+        packed = True
         for t in tables:
-            if t.data_ptr() != end or t.untyped_storage().data_ptr() != t0.untyped_storage().data_ptr():
-                ok = False
+            if t.data_ptr() != end or not same_storage(t):
+                packed = False
                 break
             end += t.numel() * 4
-    if ok:
-        n = sum(t.shape[0] for t in tables)
-        return t0.detach().as_strided((n, d), (d, 1))
-    return torch.cat([t.detach() for t in tables], dim=0)
+        if packed:
+            return t0.detach().as_strided((n, d), (d, 1)), None
+        if len(tables) == 3:
+            u, mid, b = tables
+            gap = (u.numel() + mid.numel()) * 4
+            room = t0.untyped_storage().nbytes() - (t0.data_ptr() - t0.untyped_storage().data_ptr())
+            if same_storage(b) and b.data_ptr() == u.data_ptr() + gap and room >= n * d * 4:
+                return (t0.detach().as_strided((n, d), (d, 1), t0.storage_offset()),
+                        (mid.detach(), u.shape[0]))
+    return torch.cat([t.detach() for t in tables], dim=0), None
 
 
 class FusionProjFunction(torch.autograd.Function):

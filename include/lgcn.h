@@ -33,7 +33,7 @@ typedef struct CUstream_st *lgcn_stream_t; /* == cudaStream_t */
 #define LGCN_API
 #endif
 
-#define LGCN_ABI_VERSION 5
+#define LGCN_ABI_VERSION 6
 
 #define LGCN_E_BAD_DIM   (-1) /* embedding dim not supported              */
 #define LGCN_E_BAD_ARG   (-2) /* null pointer / negative size / bad mode  */
@@ -144,6 +144,20 @@ typedef struct lgcn_spmm_args {
      * (and for long rows), 0 for the others, and does NOT write the all-zero rows of y -- the
      * consumer must read y under y_rowflag (it is the next hop's x_rowflag).  [n_rows]. */
     uint8_t       *y_rowflag;
+    /* Layer-0 override (LightGCN_Fusion: the item rows of layer 0 are the projected rows H, the
+     * other rows the raw tables -- reference models/lightgcn_fusion.py:45-52 builds that table with
+     * torch.cat every forward).  Rows c in [alt_begin, alt_begin + alt_rows) are read from
+     * x_alt[(c - alt_begin) * d ...] instead of the main table:
+     *   LGCN_SPMM_F_ALT_X       for the gathered rows of x (dense gathers only, no x_rowflag),
+     *   LGCN_SPMM_F_ALT_LAYER0  for layers[0] of the MEAN epilogue.
+     * NULL / no flag = none. */
+    const float   *x_alt;
+    int64_t        alt_begin, alt_rows;
+    /* ADAM only: rows r in [skip_begin, skip_begin + skip_rows) are NOT updated (their layer-0 rows
+     * are produced by the fusion projection, not by p); their gradient  addend + A x  (addend2 is
+     * not added) is stored to g_skip[(r - skip_begin) * d ...] for the projection's backward. */
+    float         *g_skip;
+    int64_t        skip_begin, skip_rows;
 } lgcn_spmm_args;
 
 /* tables do not fit L2: stream entries / outputs / epilogue operands with L2 evict_first so
@@ -153,8 +167,10 @@ typedef struct lgcn_spmm_args {
 #define LGCN_SPMM_F_NO_RING 2       /* register-batch chunk kernel only                      */
 #define LGCN_SPMM_F_BIG_PATH 4      /* large-graph kernels even when the graph is small      */
 #define LGCN_SPMM_F_COLD_FIRST 8    /* gathers of unclassified columns use evict_first too   */
-#define LGCN_SPMM_F_FORCE_RING 16   /* cp.async ring kernel for the ADAM epilogue too        */
+#define LGCN_SPMM_F_FORCE_RING 16   /* (no-op since ABI v5: the ring kernel serves ADAM too)  */
 #define LGCN_SPMM_F_NO_PREFETCH 32  /* no L2 prefetch of the epilogue operands (A/B only)    */
+#define LGCN_SPMM_F_ALT_X 64        /* gathers of rows in the alt range read x_alt           */
+#define LGCN_SPMM_F_ALT_LAYER0 128  /* MEAN: layers[0] rows in the alt range read x_alt      */
 
 #define LGCN_SPMM_PLAIN 0 /* y = A x                                                    */
 #define LGCN_SPMM_ADD   1 /* y = addend + A x              (Horner backward hop)        */

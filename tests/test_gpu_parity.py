@@ -214,6 +214,65 @@ def test_spmm_large_graph_kernels_bit_exact(dev, d, kernel):
         ops.SPMM_FLAGS_EXTRA, ops.HOT_BYTES = old, old_hot
 
 
+@pytest.mark.parametrize("d", [16, 64, 128])
+@pytest.mark.parametrize("path", ["small", "ring", "chunk"])
+def test_spmm_layer0_override_and_adam_row_skip(dev, d, path):
+    """LightGCN_Fusion plumbing of lgcn_spmm: ``x_alt`` (the item rows of layer 0 come from the
+    projected block, reference models/lightgcn_fusion.py:52 without the concat) must equal the
+    same call on the materialised table BIT FOR BIT in every kernel and mode; the ADAM hop's row
+    skip leaves the skipped rows' p / m / v alone, hands their gradient on, and updates the others
+    exactly like the unskipped call."""
+    from gcn_recommendation_b200 import _lib, ops, synth
+    from gcn_recommendation_b200.graph import NormAdjCSR
+    U, I, B = 1013, 1511, 3
+    inter = synth.generate((U, I, B, 26_000), seed=11 + d)
+    tu, ti, _, _ = inter.split_validation()
+    N = U + I + B
+    gen = torch.Generator(device=dev).manual_seed(d)
+    X = torch.randn((N, d), device=dev, generator=gen)
+    H = torch.randn((I, d), device=dev, generator=gen)
+    A1 = torch.randn((N, d), device=dev, generator=gen)
+    A2 = torch.randn((N, d), device=dev, generator=gen)
+    Xcat = X.clone()
+    Xcat[U:U + I] = H
+    alt = (H, U)
+    old = ops.SPMM_FLAGS_EXTRA
+    ops.SPMM_FLAGS_EXTRA = {"small": 0, "ring": _lib.SPMM_F_BIG_PATH, "chunk": _lib.SPMM_F_BIG_PATH | _lib.SPMM_F_NO_RING}[path]
+    try:
+        csr = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev, long_row_threshold=48, seg_len=32)
+        assert csr.n_long > 0
+        E1 = ops.spmm(csr, Xcat)
+        assert torch.equal(ops.spmm(csr, X, x_alt=alt), E1)
+        assert torch.equal(ops.spmm(csr, X, addend=A1, x_alt=alt), ops.spmm(csr, Xcat, addend=A1))
+        assert torch.equal(ops.spmm(csr, X, mean_layers=[X], x_alt=alt, layer0_alt=alt),
+                           ops.spmm(csr, Xcat, mean_layers=[Xcat]))                      # K = 1
+        assert torch.equal(ops.spmm(csr, E1, mean_layers=[X, E1], layer0_alt=alt),
+                           ops.spmm(csr, E1, mean_layers=[Xcat, E1]))                    # K = 2
+        assert torch.equal(ops.propagate(csr, X, 3, alt=alt), ops.propagate(csr, Xcat, 3))
+        with pytest.raises(_lib.LgcnError):
+            ops.spmm(csr, X, addend=A1, x_rowflag=torch.ones(N + 32, dtype=torch.uint8, device=dev),
+                     zero_row=torch.zeros(256, device=dev), x_alt=alt)
+        # ADAM row skip
+        sc = torch.tensor([1e-3 / (1 - 0.9 ** 2), (1 - 0.999 ** 2) ** 0.5], device=dev)
+        p0 = torch.randn((N, d), device=dev, generator=gen)
+        m0 = torch.randn((N, d), device=dev, generator=gen) * 0.01
+        v0 = torch.rand((N, d), device=dev, generator=gen) * 1e-3 + 1e-5
+        pf, mf, vf = p0.clone(), m0.clone(), v0.clone()
+        ops.spmm_adam(csr, X, pf, mf, vf, sc, addend=A1, addend2=A2)                     # every row
+        g1 = torch.empty((N, d), device=dev)
+        ops.spmm_adam(csr, X, p0.clone(), m0.clone(), v0.clone(), sc, addend=A1, g_out=g1)  # A x + A1
+        ps, ms, vs = p0.clone(), m0.clone(), v0.clone()
+        gs = torch.full((I, d), float("nan"), device=dev)
+        ops.spmm_adam(csr, X, ps, ms, vs, sc, addend=A1, addend2=A2, skip=(gs, U))
+        inside = torch.zeros(N, dtype=torch.bool, device=dev)
+        inside[U:U + I] = True
+        for got, full, init in ((ps, pf, p0), (ms, mf, m0), (vs, vf, v0)):
+            assert torch.equal(got[~inside], full[~inside]) and torch.equal(got[inside], init[inside])
+        assert torch.equal(gs, g1[U:U + I])
+    finally:
+        ops.SPMM_FLAGS_EXTRA = old
+
+
 @pytest.mark.parametrize("d", [64, 128])
 def test_spmm_long_row_plan_within_tolerance(dev, d):
     """Rows longer than the threshold are summed segment-wise: deterministic, <= 1e-5."""

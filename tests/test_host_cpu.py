@@ -284,7 +284,9 @@ def test_host_only_plan_queries():
     assert name(70_840, 64, _lib.SPMM_PLAIN) == "spmm_chunk_kernel<64,plain,4-row chunks,nohints>"
     assert name(14_700_001, 128, _lib.SPMM_PLAIN, _lib.SPMM_F_STREAM_HINTS) == "spmm_ring_kernel<128,plain,hints>"
     assert name(14_700_001, 16, _lib.SPMM_MEAN, _lib.SPMM_F_STREAM_HINTS) == "spmm_ring_kernel<16,mean,hints>"
-    assert name(14_700_001, 128, _lib.SPMM_ADAM, _lib.SPMM_F_STREAM_HINTS).startswith("spmm_chunk_kernel<128,adam,16-row")
+    assert name(14_700_001, 128, _lib.SPMM_ADAM, _lib.SPMM_F_STREAM_HINTS) == "spmm_ring_kernel<128,adam,hints>"
+    assert name(14_700_001, 128, _lib.SPMM_ADAM, _lib.SPMM_F_STREAM_HINTS | _lib.SPMM_F_NO_RING).startswith(
+        "spmm_chunk_kernel<128,adam,16-row")
     assert name(14_700_001, 128, _lib.SPMM_ADD, _lib.SPMM_F_STREAM_HINTS, 1) == "spmm_live_kernel<128,hints>"
     assert lib.lgcn_spmm_kernel_name(10, 48, 0, 0, 0, buf, 128) == -1                   # LGCN_E_BAD_DIM
     assert lib.lgcn_spmm_kernel_name(10, 64, 9, 0, 0, buf, 128) == -2                   # LGCN_E_BAD_ARG
