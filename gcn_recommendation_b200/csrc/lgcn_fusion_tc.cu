@@ -168,21 +168,26 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
                 xb[j] = ld_nc_f4(W + (size_t)r * kin + k0 + ((task & 1) * 4 + pq) * 4);
             }
         };
-        // three register buffers: chunks i (being stored), i+1 and i+2 (in flight)
+        // Three register buffers used IN PLACE: a buffer is refilled with the chunk three ahead right
+        // after it has been stored (no register copies that wait for the newest load).  Measured
+        // neutral (11.5 -> 11.4 ms): the loaders are not latency bound -- ncu r02 shows the LSU data
+        // pipe at 96 % (l1tex__data_pipe_lsu_wavefronts), three quarters of it the wavefronts of these
+        // global loads (8 rows x 64 bytes per LDG.128), see profiles/r02_fusion_notes.txt.
         float4 xa[4], xb[NBT], ya[4], yb[NBT], za[4], zb[NBT];
         auto advance = [&](int64_t &t, int &c_) {
             if (++c_ == n_chunks) { c_ = 0; t += gridDim.x; }
         };
-        int64_t tile = blockIdx.x, t1 = tile, t2;
-        int ch = 0, c1 = 0, c2;
-        if (tile < n_tiles) load_chunk(tile, 0, xa, xb);
-        advance(t1, c1);
-        if (t1 < n_tiles) load_chunk(t1, c1, ya, yb);
-        t2 = t1; c2 = c1;
+        int64_t tile = blockIdx.x, tload = blockIdx.x;            // store cursor / load cursor
+        int ch = 0, cload = 0;
+        auto load_next = [&](float4 (&a)[4], float4 (&b)[NBT]) {
+            if (tload < n_tiles) load_chunk(tload, cload, a, b);
+            advance(tload, cload);
+        };
+        load_next(xa, xb);
+        load_next(ya, yb);
+        load_next(za, zb);
         uint32_t it = 0;
-        while (tile < n_tiles) {
-            advance(t2, c2);
-            if (t2 < n_tiles) load_chunk(t2, c2, za, zb);
+        auto step = [&](float4 (&a)[4], float4 (&b)[NBT]) {
             const int s = it % NSTAGE;
             mbar_wait(smem_u32(&sm.empty[s]), ((it / NSTAGE) & 1) ^ 1);
 #pragma unroll
@@ -191,7 +196,7 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
                 const int r = (task >> 1) * 8 + rl;
                 const int kq = (task & 1) * 4 + pq;
                 const int off = kq * (MT / 8) * 32 + (r >> 3) * 32 + (r & 7) * 4;   // floats
-                split_store(&sm.A[s][0][off], &sm.A[s][1][off], xa[j]);
+                split_store(&sm.A[s][0][off], &sm.A[s][1][off], a[j]);
             }
 #pragma unroll
             for (int j = 0; j < NBT; ++j) {
@@ -199,20 +204,22 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
                 const int r = (task >> 1) * 8 + rl;
                 const int kq = (task & 1) * 4 + pq;
                 const int off = kq * (D / 8) * 32 + (r >> 3) * 32 + (r & 7) * 4;
-                split_store(&sm.B[s][0][off], &sm.B[s][1][off], xb[j]);
+                split_store(&sm.B[s][0][off], &sm.B[s][1][off], b[j]);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&sm.full[s]));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { xa[j] = ya[j]; ya[j] = za[j]; }
-#pragma unroll
-            for (int j = 0; j < NBT; ++j) { xb[j] = yb[j]; yb[j] = zb[j]; }
-            tile = t1; ch = c1;
-            t1 = t2; c1 = c2;
+            load_next(a, b);                                  // refill in place: the chunk 3 ahead
+            advance(tile, ch);
             ++it;
+        };
+        while (tile < n_tiles) {
+            step(xa, xb);
+            if (tile >= n_tiles) break;
+            step(ya, yb);
+            if (tile >= n_tiles) break;
+            step(za, zb);
         }
-        (void)ch;
     } else if (warp == LOADER_WARPS) {
         // ===== MMA issuer =====
         if (lane == 0) {
@@ -405,6 +412,8 @@ fusion_bwd_w_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ 
                 xh[j] = make_float4(h[0], h[1], h[2], h[3]);
             }
         };
+        // (an in-place two-buffer rotation without the register copies below was measured SLOWER here:
+        // 20.1 vs 16.9 ms at 4.4 M items -- profiles/r02_fusion_notes.txt)
         float4 xa[NAT], xg[NBT], xh[NBT], ya[NAT], yg[NBT], yh[NBT];
         if (0 < n_chunks) load_chunk(0, xa, xg, xh);
         for (int ch = 0; ch < n_chunks; ++ch) {

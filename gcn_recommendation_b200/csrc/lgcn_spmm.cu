@@ -571,6 +571,22 @@ struct RingCfg {
     static_assert(R % 4 == 0, "chunk rows");
 };
 
+// The live-list kernel spends its time in the rowptr -> {col,val} -> flag start-up chain of a chunk,
+// not in gathers: more rows per worker amortise that chain (LGCN_LIVE_R rows, one row end per lane).
+#ifndef LGCN_LIVE_R
+#define LGCN_LIVE_R 8
+#endif
+template <int D>
+struct LiveCfg {
+    using G = RowGeom<D>;
+    static constexpr int R = G::LANES < LGCN_LIVE_R ? G::LANES : LGCN_LIVE_R;
+    static constexpr int S = RingCfg<D>::SL;
+    static constexpr int WORKERS = kRingWarps * G::GROUPS;
+    static constexpr int ROWS_PER_CTA = WORKERS * R;
+    static constexpr size_t SMEM = (size_t)WORKERS * (R + S) * D * sizeof(float);
+    static_assert(R % 4 == 0, "chunk rows");
+};
+
 template <int D, int MODE, bool HINT, int NLM = 8>
 __global__ void __launch_bounds__(kRingWarps * 32)
 spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
@@ -746,8 +762,8 @@ template <int D, bool HINT>
 __global__ void __launch_bounds__(kRingWarps * 32)
 spmm_live_kernel(const __grid_constant__ lgcn_spmm_args a) {
     using G = RowGeom<D>;
-    using C = RingCfg<D>;
-    constexpr int L = G::LANES, S = C::SL;
+    using C = LiveCfg<D>;
+    constexpr int L = G::LANES, S = C::S;
     const uint64_t pol = HINT ? policy_evict_first() : 0ull;
     extern __shared__ __align__(16) float ring_smem[];
     const int lane = threadIdx.x & 31;
@@ -1046,7 +1062,7 @@ static int launch_chunks(const lgcn_spmm_args &a, cudaStream_t st) {
 
 template <int D, bool HINT>
 static int launch_live(const lgcn_spmm_args &a, cudaStream_t st) {
-    using C = RingCfg<D>;
+    using C = LiveCfg<D>;
     LGCN_OPT_IN_SMEM((spmm_live_kernel<D, HINT>), C::SMEM);
     const int64_t gb = (a.n_rows + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
     if (gb > 0x7fffffffLL) return LGCN_E_TOO_LARGE;
