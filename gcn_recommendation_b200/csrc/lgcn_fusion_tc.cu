@@ -141,20 +141,23 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
 
     if (warp < LOADER_WARPS) {
         // ===== loaders: fp32 rows -> hi/lo tf32 in the canonical layout =====
-        // a warp task = 8 rows x 4 pieces (64 B per row): lanes 0-7 take rows, lane/8 the piece,
-        // so global reads are full sectors and the 16-byte smem stores are conflict free.
-        // The loads of chunk i+1 are issued before chunk i is split and stored (register
-        // prefetch): a loader warp would otherwise serialise on one HBM latency per chunk.
-        const int rl = lane & 7, pq = lane >> 3;
-        constexpr int NBT = (D / 8) * 2 / LOADER_WARPS;          // B tasks per warp
+        // A warp works on PAIRS of tasks = 8 rows x the chunk's 128 bytes.  Loads: lane (rho = lane / 8,
+        // kap = lane % 8) reads the 16-byte piece kap of row rho (task 2p) and of row rho + 4 (task
+        // 2p + 1): every LDG.128 covers 4 rows x 128 contiguous bytes -- four full lines.  (Round 1 read
+        // 8 rows x 64 bytes per instruction; ncu r02: the LSU data pipe was 96 % busy, three quarters of
+        // it the wavefronts of those loads.)  Stores: each lane stores its OWN two pieces, choosing per
+        // instruction which one goes -- lanes kap < 4 store rows rho first and rho + 4 second, lanes
+        // kap >= 4 the other way round -- so one store instruction writes 4 K-columns x bytes 0-63 and
+        // 4 K-columns x bytes 64-127 of the 128-byte core-matrix row blocks: all 32 banks, conflict free.
+        const int rho = lane >> 3, kap = lane & 7;
+        constexpr int NBT = (D / 8) * 2 / LOADER_WARPS;          // B tasks per warp (pairs: NBT / 2)
+        static_assert(NBT % 2 == 0, "loader tasks come in pairs");
         auto load_chunk = [&](int64_t tile, int ch, float4 (&xa)[4], float4 (&xb)[NBT]) {
             const int64_t i0 = tile * MT;
-            const int k0 = ch * KC;
+            const int k = ch * KC + kap * 4;                     // first float of this lane's piece
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int task = warp * 4 + j;
-                const int r = (task >> 1) * 8 + rl;
-                const int k = k0 + ((task & 1) * 4 + pq) * 4;
+                const int r = (warp * 2 + (j >> 1)) * 8 + (j & 1) * 4 + rho;
                 const int64_t item = i0 + r;
                 xa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (item < n_items)
@@ -163,9 +166,22 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
             }
 #pragma unroll
             for (int j = 0; j < NBT; ++j) {
-                const int task = warp * NBT + j;
-                const int r = (task >> 1) * 8 + rl;
-                xb[j] = ld_nc_f4(W + (size_t)r * kin + k0 + ((task & 1) * 4 + pq) * 4);
+                const int r = (warp * (NBT / 2) + (j >> 1)) * 8 + (j & 1) * 4 + rho;
+                xb[j] = ld_nc_f4(W + (size_t)r * kin + k);
+            }
+        };
+        // store one pair: `lo` holds rows base+rho, `hi` rows base+4+rho (piece kap of each)
+        auto store_pair = [&](float *hi_dst, float *lo_dst, int rows8, int base8, const float4 &lo, const float4 &hi) {
+            const bool first_low = kap < 4;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const bool low_rows = (h == 0) == first_low;      // which half of the 8 rows this store takes
+                const int r = base8 * 8 + (low_rows ? 0 : 4) + rho;
+                const int off = kap * rows8 * 32 + (r >> 3) * 32 + (r & 7) * 4;   // floats
+                float4 v;                                         // value selects (no addressable temporaries)
+                v.x = low_rows ? lo.x : hi.x; v.y = low_rows ? lo.y : hi.y;
+                v.z = low_rows ? lo.z : hi.z; v.w = low_rows ? lo.w : hi.w;
+                split_store(hi_dst + off, lo_dst + off, v);
             }
         };
         // Three register buffers used IN PLACE: a buffer is refilled with the chunk three ahead right
@@ -191,21 +207,11 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
             const int s = it % NSTAGE;
             mbar_wait(smem_u32(&sm.empty[s]), ((it / NSTAGE) & 1) ^ 1);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int task = warp * 4 + j;
-                const int r = (task >> 1) * 8 + rl;
-                const int kq = (task & 1) * 4 + pq;
-                const int off = kq * (MT / 8) * 32 + (r >> 3) * 32 + (r & 7) * 4;   // floats
-                split_store(&sm.A[s][0][off], &sm.A[s][1][off], a[j]);
-            }
+            for (int jj = 0; jj < 2; ++jj)
+                store_pair(&sm.A[s][0][0], &sm.A[s][1][0], MT / 8, warp * 2 + jj, a[2 * jj], a[2 * jj + 1]);
 #pragma unroll
-            for (int j = 0; j < NBT; ++j) {
-                const int task = warp * NBT + j;
-                const int r = (task >> 1) * 8 + rl;
-                const int kq = (task & 1) * 4 + pq;
-                const int off = kq * (D / 8) * 32 + (r >> 3) * 32 + (r & 7) * 4;
-                split_store(&sm.B[s][0][off], &sm.B[s][1][off], b[j]);
-            }
+            for (int jj = 0; jj < NBT / 2; ++jj)
+                store_pair(&sm.B[s][0][0], &sm.B[s][1][0], D / 8, warp * (NBT / 2) + jj, b[2 * jj], b[2 * jj + 1]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&sm.full[s]));
