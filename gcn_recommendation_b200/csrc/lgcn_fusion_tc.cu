@@ -8,8 +8,8 @@
 // materialised and the 13.5 GB content matrix is streamed exactly once.
 //
 // CTA (persistent over 128-item tiles): 8 loader warps read fp32 rows (E_id for k < d, content
-// for k >= d; W rows likewise), split them and write hi / lo straight into the UMMA canonical
-// K-major no-swizzle layout in shared memory (generic-proxy stores + fence.proxy.async); one
+// for k >= d; W rows likewise), split them and write hi / lo straight into the UMMA K-major
+// SWIZZLE_128B layout in shared memory (generic-proxy stores + fence.proxy.async); one
 // thread issues 12 tcgen05.mma.kind::tf32 (128 x d x 8) per 32-wide K chunk into one of two TMEM
 // accumulators; 4 epilogue warps (thread <-> item <-> TMEM lane) add the bias, apply the leaky
 // relu and store the row.  3-stage ring, mbarrier full/empty, tcgen05.commit.
@@ -21,7 +21,7 @@ namespace lgcn {
 namespace ftc {
 
 constexpr int MT = 128;            // items per tile (UMMA M)
-constexpr int KC = 32;             // K chunk (floats) = 8 core-matrix columns of 4 tf32
+constexpr int KC = 32;             // K chunk (floats) = one 128-byte swizzle-atom row = 4 K=8 instructions
 constexpr int NSTAGE = 3;
 constexpr int LOADER_WARPS = 8;
 constexpr int kThreads = (LOADER_WARPS + 1 + 4) * 32;   // loaders, MMA issuer, epilogue
@@ -81,13 +81,26 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo, 
     return d;
 }
 // D fp32 (bits 4-5 = 1), A/B tf32 (format 2 at bits 7-9 / 10-12), K-major, N>>3 at 17, M>>4 at 24
+// K-major, SWIZZLE_128B: a row is 128 contiguous bytes (32 tf32), its 16-byte unit q stored at
+// position q ^ (row & 7); 8-row groups are 1024 bytes apart (SBO), the leading offset is unused.
+// The buffer must be 1024-byte aligned (the XOR acts on absolute shared-memory address bits); a
+// K = 8 instruction advances the start address by 32 bytes inside the swizzle atom.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((1024u >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
 }
 
 template <int D>
 struct Smem {
-    // per stage: [hi | lo] for A (128 x 32) and B (D x 32), canonical layout
+    // per stage: [hi | lo] for A (128 x 32) and B (D x 32), K-major SWIZZLE_128B (128-byte rows)
     float A[NSTAGE][2][MT * KC];
     float B[NSTAGE][2][D * KC];
     unsigned long long full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2];
@@ -109,15 +122,13 @@ __global__ void __launch_bounds__(kThreads, 1)
 fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm,
                      const float *__restrict__ W, const float *__restrict__ bias, int64_t n_items,
                      int c, float *__restrict__ H) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem<D> &sm = *reinterpret_cast<Smem<D> *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kin = D + c;
     const int n_chunks = kin / KC;
     const int64_t n_tiles = (n_items + MT - 1) / MT;
-    constexpr uint32_t SBO = 128;
-    constexpr uint32_t LBO_A = (MT / 8) * 128;      // bytes between K columns of A
-    constexpr uint32_t LBO_B = (D / 8) * 128;
+    if (smem_u32(smem_raw) & 1023u) __trap();       // SWIZZLE_128B operands need 1024-byte alignment
     constexpr uint32_t IDESC = make_idesc(D);
     constexpr int TMEM_COLS = 2 * D < 32 ? 32 : 2 * D;
 
@@ -140,49 +151,36 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
     const uint32_t tmem_base = sm.tmem_base;
 
     if (warp < LOADER_WARPS) {
-        // ===== loaders: fp32 rows -> hi/lo tf32 in the canonical layout =====
-        // A warp works on PAIRS of tasks = 8 rows x the chunk's 128 bytes.  Loads: lane (rho = lane / 8,
-        // kap = lane % 8) reads the 16-byte piece kap of row rho (task 2p) and of row rho + 4 (task
-        // 2p + 1): every LDG.128 covers 4 rows x 128 contiguous bytes -- four full lines.  (Round 1 read
-        // 8 rows x 64 bytes per instruction; ncu r02: the LSU data pipe was 96 % busy, three quarters of
-        // it the wavefronts of those loads.)  Stores: each lane stores its OWN two pieces, choosing per
-        // instruction which one goes -- lanes kap < 4 store rows rho first and rho + 4 second, lanes
-        // kap >= 4 the other way round -- so one store instruction writes 4 K-columns x bytes 0-63 and
-        // 4 K-columns x bytes 64-127 of the 128-byte core-matrix row blocks: all 32 banks, conflict free.
+        // ===== loaders: fp32 rows -> hi/lo tf32 in the SWIZZLE_128B K-major layout =====
+        // A chunk is 32 floats = 128 bytes of a row = one swizzle atom row.  Lane (rho = lane / 8,
+        // kap = lane % 8) reads the 16-byte piece kap of rows rho and rho + 4 of each 8-row group:
+        // every LDG.128 covers 4 rows x 128 contiguous bytes (four full lines; round 1 read 8 rows x
+        // 64 bytes per instruction and ran the LSU data pipe at 96 %).  A 128-bit shared store is
+        // served per QUARTER warp, so the 8 lanes of one row must hit 32 distinct banks: with the
+        // no-swizzle canonical layout (a row's pieces 2 KB apart) they hit the same 4 banks (ncu r02:
+        // 396 M conflict wavefronts); in the swizzled layout they write one permuted 128-byte row.
         const int rho = lane >> 3, kap = lane & 7;
-        constexpr int NBT = (D / 8) * 2 / LOADER_WARPS;          // B tasks per warp (pairs: NBT / 2)
+        constexpr int NBT = (D / 8) * 2 / LOADER_WARPS;          // B half-groups (4 rows) per warp
         static_assert(NBT % 2 == 0, "loader tasks come in pairs");
+        auto a_row = [&](int j) { return (warp * 2 + (j >> 1)) * 8 + (j & 1) * 4 + rho; };
+        auto b_row = [&](int j) { return (warp * (NBT / 2) + (j >> 1)) * 8 + (j & 1) * 4 + rho; };
         auto load_chunk = [&](int64_t tile, int ch, float4 (&xa)[4], float4 (&xb)[NBT]) {
             const int64_t i0 = tile * MT;
             const int k = ch * KC + kap * 4;                     // first float of this lane's piece
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int r = (warp * 2 + (j >> 1)) * 8 + (j & 1) * 4 + rho;
-                const int64_t item = i0 + r;
+                const int64_t item = i0 + a_row(j);
                 xa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (item < n_items)
                     xa[j] = (k < D) ? ld_nc_f4(Eid + (size_t)item * D + k)
                                     : ld_stream_f4(Cm + (size_t)item * c + (k - D));
             }
 #pragma unroll
-            for (int j = 0; j < NBT; ++j) {
-                const int r = (warp * (NBT / 2) + (j >> 1)) * 8 + (j & 1) * 4 + rho;
-                xb[j] = ld_nc_f4(W + (size_t)r * kin + k);
-            }
+            for (int j = 0; j < NBT; ++j) xb[j] = ld_nc_f4(W + (size_t)b_row(j) * kin + k);
         };
-        // store one pair: `lo` holds rows base+rho, `hi` rows base+4+rho (piece kap of each)
-        auto store_pair = [&](float *hi_dst, float *lo_dst, int rows8, int base8, const float4 &lo, const float4 &hi) {
-            const bool first_low = kap < 4;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const bool low_rows = (h == 0) == first_low;      // which half of the 8 rows this store takes
-                const int r = base8 * 8 + (low_rows ? 0 : 4) + rho;
-                const int off = kap * rows8 * 32 + (r >> 3) * 32 + (r & 7) * 4;   // floats
-                float4 v;                                         // value selects (no addressable temporaries)
-                v.x = low_rows ? lo.x : hi.x; v.y = low_rows ? lo.y : hi.y;
-                v.z = low_rows ? lo.z : hi.z; v.w = low_rows ? lo.w : hi.w;
-                split_store(hi_dst + off, lo_dst + off, v);
-            }
+        auto store_piece = [&](float *hi_dst, float *lo_dst, int r, const float4 &x) {
+            const int off = r * KC + ((kap ^ (r & 7)) << 2);      // floats
+            split_store(hi_dst + off, lo_dst + off, x);
         };
         // Three register buffers used IN PLACE: a buffer is refilled with the chunk three ahead right
         // after it has been stored (no register copies that wait for the newest load).  Measured
@@ -207,11 +205,9 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
             const int s = it % NSTAGE;
             mbar_wait(smem_u32(&sm.empty[s]), ((it / NSTAGE) & 1) ^ 1);
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj)
-                store_pair(&sm.A[s][0][0], &sm.A[s][1][0], MT / 8, warp * 2 + jj, a[2 * jj], a[2 * jj + 1]);
+            for (int j = 0; j < 4; ++j) store_piece(&sm.A[s][0][0], &sm.A[s][1][0], a_row(j), a[j]);
 #pragma unroll
-            for (int jj = 0; jj < NBT / 2; ++jj)
-                store_pair(&sm.B[s][0][0], &sm.B[s][1][0], D / 8, warp * (NBT / 2) + jj, b[2 * jj], b[2 * jj + 1]);
+            for (int j = 0; j < NBT; ++j) store_piece(&sm.B[s][0][0], &sm.B[s][1][0], b_row(j), b[j]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&sm.full[s]));
@@ -242,10 +238,10 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
                     const uint32_t b_hi = smem_u32(&sm.B[s][0][0]), b_lo = smem_u32(&sm.B[s][1][0]);
 #pragma unroll
                     for (int kk = 0; kk < KC / 8; ++kk) {
-                        const uint64_t ah = make_smem_desc(a_hi + kk * 2 * LBO_A, LBO_A, SBO);
-                        const uint64_t al = make_smem_desc(a_lo + kk * 2 * LBO_A, LBO_A, SBO);
-                        const uint64_t bh = make_smem_desc(b_hi + kk * 2 * LBO_B, LBO_B, SBO);
-                        const uint64_t bl = make_smem_desc(b_lo + kk * 2 * LBO_B, LBO_B, SBO);
+                        const uint64_t ah = make_smem_desc_sw128(a_hi + kk * 32);
+                        const uint64_t al = make_smem_desc_sw128(a_lo + kk * 32);
+                        const uint64_t bh = make_smem_desc_sw128(b_hi + kk * 32);
+                        const uint64_t bl = make_smem_desc_sw128(b_lo + kk * 32);
                         const uint32_t d_addr = tmem_base + acc * D;
                         tc_mma_tf32(d_addr, al, bh, IDESC, (ch > 0 || kk > 0) ? 1u : 0u);   // small terms first
                         tc_mma_tf32(d_addr, ah, bl, IDESC, 1u);
