@@ -14,6 +14,8 @@ extern "C" int lgcn_fusion_fwd_tc_try(const float *Eid, const float *C, const fl
 extern "C" int lgcn_fusion_bwd_w_tc_try(const float *Eid, const float *C, const float *H, const float *gH,
                                         int64_t n_items, int32_t d, int32_t c, float *gW, float *gb,
                                         cudaStream_t st);
+extern "C" int lgcn_fusion_bwd_eid_tc_try(const float *W, const float *H, const float *gH, int64_t n_items,
+                                          int32_t d, int32_t c, float *gEid, cudaStream_t st);
 static int g_fusion_force_simt = 0;
 
 namespace lgcn {
@@ -250,9 +252,14 @@ template <int D>
 static int fusion_bwd_launch(const float *Eid, const float *C, const float *W, const float *H,
                              const float *gH, int64_t n_items, int c, float *gEid, float *gW,
                              float *gb, cudaStream_t st) {
-    const int64_t blocks = (n_items + FM - 1) / FM;
-    fusion_bwd_eid_kernel<D><<<(unsigned)blocks, kFusThreads, 0, st>>>(W, H, gH, n_items, c, gEid);
-    LGCN_LAUNCH_CHECK();
+    int eid_rc = -100;
+    if (!g_fusion_force_simt) eid_rc = lgcn_fusion_bwd_eid_tc_try(W, H, gH, n_items, D, c, gEid, st);
+    if (eid_rc > 0 || (eid_rc < 0 && eid_rc != -100)) return eid_rc;
+    if (eid_rc == -100) {
+        const int64_t blocks = (n_items + FM - 1) / FM;
+        fusion_bwd_eid_kernel<D><<<(unsigned)blocks, kFusThreads, 0, st>>>(W, H, gH, n_items, c, gEid);
+        LGCN_LAUNCH_CHECK();
+    }
     if (!g_fusion_force_simt) {             // tensor-core 3xTF32 path (lgcn_fusion_tc.cu)
         const int rc = lgcn_fusion_bwd_w_tc_try(Eid, C, H, gH, n_items, D, c, gW, gb, st);
         if (rc != -100) return rc;

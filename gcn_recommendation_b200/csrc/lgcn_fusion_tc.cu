@@ -117,7 +117,14 @@ __device__ __forceinline__ void split_store(float *hi_dst, float *lo_dst, const 
     *reinterpret_cast<float4 *>(lo_dst) = l;
 }
 
-template <int D>
+// EID = true turns the same pipeline into the backward of the item-id block
+// (models/lightgcn_fusion.py:45-49 under autograd):
+//     gEid[i, k] = sum_o gpre[i, o] W[o, k]  (k < d),   gpre = gH * leaky'(H)
+// A rows are gpre rows computed on load (`Eid` := gH, `Cm` := H, K = o: d / 32 chunks); B row k is
+// column k of W (the loader transposes by its load pattern: a lane owns one k and reads it for 4
+// consecutive o, every LDG.32 a coalesced 128-byte piece of a W row); the epilogue stores the
+// accumulator as it is.
+template <int D, bool EID>
 __global__ void __launch_bounds__(kThreads, 1)
 fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm,
                      const float *__restrict__ W, const float *__restrict__ bias, int64_t n_items,
@@ -126,7 +133,7 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
     Smem<D> &sm = *reinterpret_cast<Smem<D> *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kin = D + c;
-    const int n_chunks = kin / KC;
+    const int n_chunks = EID ? D / KC : kin / KC;
     const int64_t n_tiles = (n_items + MT - 1) / MT;
     if (smem_u32(smem_raw) & 1023u) __trap();       // SWIZZLE_128B operands need 1024-byte alignment
     constexpr uint32_t IDESC = make_idesc(D);
@@ -171,12 +178,30 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
             for (int j = 0; j < 4; ++j) {
                 const int64_t item = i0 + a_row(j);
                 xa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (item < n_items)
-                    xa[j] = (k < D) ? ld_nc_f4(Eid + (size_t)item * D + k)
-                                    : ld_stream_f4(Cm + (size_t)item * c + (k - D));
+                if (item < n_items) {
+                    if constexpr (EID) {
+                        float4 g = ld_stream_f4(Eid + (size_t)item * D + k);
+                        const float4 h = ld_stream_f4(Cm + (size_t)item * D + k);
+                        g.x *= h.x > 0.f ? 1.f : 0.01f; g.y *= h.y > 0.f ? 1.f : 0.01f;
+                        g.z *= h.z > 0.f ? 1.f : 0.01f; g.w *= h.w > 0.f ? 1.f : 0.01f;
+                        xa[j] = g;
+                    } else {
+                        xa[j] = (k < D) ? ld_nc_f4(Eid + (size_t)item * D + k)
+                                        : ld_stream_f4(Cm + (size_t)item * c + (k - D));
+                    }
+                }
             }
 #pragma unroll
-            for (int j = 0; j < NBT; ++j) xb[j] = ld_nc_f4(W + (size_t)b_row(j) * kin + k);
+            for (int j = 0; j < NBT; ++j) {
+                if constexpr (EID) {
+                    // task t = warp * NBT + j: k block t % (D / 32), o quad t / (D / 32); lane = k in block
+                    const int t = warp * NBT + j;
+                    const float *src = W + (size_t)(ch * KC + (t / (D / 32)) * 4) * kin + (t % (D / 32)) * 32 + lane;
+                    xb[j] = make_float4(__ldg(src), __ldg(src + kin), __ldg(src + 2 * kin), __ldg(src + 3 * kin));
+                } else {
+                    xb[j] = ld_nc_f4(W + (size_t)b_row(j) * kin + k);
+                }
+            }
         };
         auto store_piece = [&](float *hi_dst, float *lo_dst, int r, const float4 &x) {
             const int off = r * KC + ((kap ^ (r & 7)) << 2);      // floats
@@ -207,7 +232,17 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
 #pragma unroll
             for (int j = 0; j < 4; ++j) store_piece(&sm.A[s][0][0], &sm.A[s][1][0], a_row(j), a[j]);
 #pragma unroll
-            for (int j = 0; j < NBT; ++j) store_piece(&sm.B[s][0][0], &sm.B[s][1][0], b_row(j), b[j]);
+            for (int j = 0; j < NBT; ++j) {
+                if constexpr (EID) {
+                    // 8 consecutive lanes = 8 consecutive rows, one unit each at 8 distinct positions
+                    const int t = warp * NBT + j;
+                    const int r = (t % (D / 32)) * 32 + lane, kq = t / (D / 32);
+                    const int off = r * KC + ((kq ^ (r & 7)) << 2);
+                    split_store(&sm.B[s][0][off], &sm.B[s][1][off], b[j]);
+                } else {
+                    store_piece(&sm.B[s][0][0], &sm.B[s][1][0], b_row(j), b[j]);
+                }
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&sm.full[s]));
@@ -270,15 +305,17 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
                     float *dst = H + (size_t)item * D + cb * 32;
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        float4 o;
-                        o.x = v[i] + __ldg(bias + cb * 32 + i);
-                        o.y = v[i + 1] + __ldg(bias + cb * 32 + i + 1);
-                        o.z = v[i + 2] + __ldg(bias + cb * 32 + i + 2);
-                        o.w = v[i + 3] + __ldg(bias + cb * 32 + i + 3);
-                        o.x = o.x > 0.f ? o.x : 0.01f * o.x;
-                        o.y = o.y > 0.f ? o.y : 0.01f * o.y;
-                        o.z = o.z > 0.f ? o.z : 0.01f * o.z;
-                        o.w = o.w > 0.f ? o.w : 0.01f * o.w;
+                        float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        if constexpr (!EID) {
+                            o.x += __ldg(bias + cb * 32 + i);
+                            o.y += __ldg(bias + cb * 32 + i + 1);
+                            o.z += __ldg(bias + cb * 32 + i + 2);
+                            o.w += __ldg(bias + cb * 32 + i + 3);
+                            o.x = o.x > 0.f ? o.x : 0.01f * o.x;
+                            o.y = o.y > 0.f ? o.y : 0.01f * o.y;
+                            o.z = o.z > 0.f ? o.z : 0.01f * o.z;
+                            o.w = o.w > 0.f ? o.w : 0.01f * o.w;
+                        }
                         st_f4(dst + i, o);
                     }
                 }
@@ -296,13 +333,13 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
     }
 }
 
-template <int D>
+template <int D, bool EID>
 int launch_fwd(const float *Eid, const float *C, const float *W, const float *b, int64_t n_items, int c,
                float *H, cudaStream_t st) {
-    LGCN_OPT_IN_SMEM((fusion_fwd_tc_kernel<D>), sizeof(Smem<D>));
+    LGCN_OPT_IN_SMEM((fusion_fwd_tc_kernel<D, EID>), sizeof(Smem<D>));
     const int64_t tiles = (n_items + MT - 1) / MT;
     const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-    fusion_fwd_tc_kernel<D><<<grid, kThreads, sizeof(Smem<D>), st>>>(Eid, C, W, b, n_items, c, H);
+    fusion_fwd_tc_kernel<D, EID><<<grid, kThreads, sizeof(Smem<D>), st>>>(Eid, C, W, b, n_items, c, H);
     LGCN_LAUNCH_CHECK();
     return 0;
 }
@@ -550,8 +587,18 @@ extern "C" __attribute__((visibility("hidden"))) int lgcn_fusion_fwd_tc_try(
     int32_t c, float *H, cudaStream_t st) {
     using namespace lgcn::ftc;
     if ((d != 64 && d != 128) || c % KC != 0 || n_items < MT) return -100;
-    return d == 64 ? launch_fwd<64>(Eid, C, W, b, n_items, c, H, st)
-                   : launch_fwd<128>(Eid, C, W, b, n_items, c, H, st);
+    return d == 64 ? launch_fwd<64, false>(Eid, C, W, b, n_items, c, H, st)
+                   : launch_fwd<128, false>(Eid, C, W, b, n_items, c, H, st);
+}
+
+// gEid of the backward pass: the forward pipeline with A = gH * leaky'(H) and B = W[:, :d]^T
+extern "C" __attribute__((visibility("hidden"))) int lgcn_fusion_bwd_eid_tc_try(
+    const float *W, const float *H, const float *gH, int64_t n_items, int32_t d, int32_t c, float *gEid,
+    cudaStream_t st) {
+    using namespace lgcn::ftc;
+    if ((d != 64 && d != 128) || n_items < MT) return -100;
+    return d == 64 ? launch_fwd<64, true>(gH, H, W, nullptr, n_items, c, gEid, st)
+                   : launch_fwd<128, true>(gH, H, W, nullptr, n_items, c, gEid, st);
 }
 
 // gW / gb of the backward pass (accumulated into the caller's zero-initialised or running buffers)

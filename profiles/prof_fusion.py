@@ -53,4 +53,8 @@ for simt in (0, 1):
     ms = timeit(lambda: ops.fusion_proj_bwd(E, C, W, H, gH, g_eid=gE, gW=gW, gb=gb))
     print(f"bwd {'simt' if simt else 'tc  '} (gE_id + gW + gb) n={n} d={d}: {ms:.2f} ms  "
           f"{(flops + 2.0 * n * d * d) / ms / 1e9:.1f} TFLOP/s (fp32-equivalent)")
+    if simt:
+        print(f"gE_id tc vs simt max rel err {(gEtc - gE).abs().max().item() / gE.abs().max().item():.2e}")
+    else:
+        gEtc = gE.clone()
 lib.lgcn_fusion_force_simt(0)
