@@ -364,6 +364,11 @@ int launch_fwd(const float *Eid, const float *C, const float *W, const float *b,
 // combined by fp32 atomics); epilogue thread <-> TMEM lane <-> feature k.
 // =================================================================================================
 constexpr int kSubChunks = 32;      // 1024 items (128 accumulations) per TMEM accumulation chain
+#ifndef LGCN_BW_LOADER_WARPS
+#define LGCN_BW_LOADER_WARPS 16     // the gW loaders are latency bound (ncu r02: long-scoreboard 3.7 per issue)
+#endif
+constexpr int BW_LOADERS = LGCN_BW_LOADER_WARPS;
+constexpr int kBwThreads = (BW_LOADERS + 1 + 4) * 32;   // loaders, MMA issuer, epilogue
 
 template <int D>
 struct SmemBw {
@@ -374,7 +379,7 @@ struct SmemBw {
 };
 
 template <int D>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kBwThreads, 1)
 fusion_bwd_w_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm,
                        const float *__restrict__ H, const float *__restrict__ gH, int64_t n_items,
                        int c, int64_t items_per_slab, float *__restrict__ gW, float *__restrict__ gb) {
@@ -394,13 +399,13 @@ fusion_bwd_w_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ 
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(smem_u32(&sm.full[s]), LOADER_WARPS);
+            mbar_init(smem_u32(&sm.full[s]), BW_LOADERS);
             mbar_init(smem_u32(&sm.empty[s]), 1);
         }
         for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&sm.tfull[b]), 1); mbar_init(smem_u32(&sm.tempty[b]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == LOADER_WARPS) {
+    if (warp == BW_LOADERS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(&sm.tmem_base)), "r"((uint32_t)TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -410,10 +415,11 @@ fusion_bwd_w_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ 
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
 
-    if (warp < LOADER_WARPS) {
+    if (warp < BW_LOADERS) {
         // ===== loaders: a warp task = 32 features (one per lane) x 4 consecutive items =====
-        constexpr int NAT = 4;                                   // A tasks per warp: 4 feature blocks x 8 item quads / 8 warps
-        constexpr int NBT = (D / 32) * (KC / 4) / LOADER_WARPS;  // B tasks per warp
+        constexpr int NAT = 32 / BW_LOADERS;                     // A tasks per warp: 4 feature blocks x 8 item quads
+        constexpr int NBT = (D / 32) * (KC / 4) / BW_LOADERS;    // B tasks per warp
+        static_assert(NAT >= 1 && NBT >= 1, "too many loader warps");
         float bsum[NBT];
 #pragma unroll
         for (int j = 0; j < NBT; ++j) bsum[j] = 0.f;
@@ -451,12 +457,30 @@ fusion_bwd_w_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ 
                 xh[j] = make_float4(h[0], h[1], h[2], h[3]);
             }
         };
-        // (an in-place two-buffer rotation without the register copies below was measured SLOWER here:
-        // 20.1 vs 16.9 ms at 4.4 M items -- profiles/r02_fusion_notes.txt)
-        float4 xa[NAT], xg[NBT], xh[NBT], ya[NAT], yg[NBT], yh[NBT];
-        if (0 < n_chunks) load_chunk(0, xa, xg, xh);
+        // Software pipeline: x = chunk ch, finished (gpre formed); r = the RAW loads of chunk ch + 1,
+        // issued one whole iteration earlier.  Per iteration: finish r into y (the only wait, for loads
+        // that have had a full store phase to arrive), re-issue r for chunk ch + 2, store x, x = y.
+        // (Round 2 history, 4.4 M items, whole backward: one-ahead loads waited for at the end of
+        // their own iteration 13.5 ms with 8 loader warps, 12.15 with 16; an in-place two-buffer
+        // rotation was slower, 20.1 vs 16.9 -- profiles/r02_fusion_notes.txt.)
+        float4 xa[NAT], xg[NBT], ra[NAT], rg[NBT], rh[NBT];
+        auto finish = [&](float4 (&da)[NAT], float4 (&dg)[NBT]) {
+#pragma unroll
+            for (int j = 0; j < NAT; ++j) da[j] = ra[j];
+#pragma unroll
+            for (int j = 0; j < NBT; ++j) {
+                float4 g = rg[j];
+                g.x *= rh[j].x > 0.f ? 1.f : 0.01f; g.y *= rh[j].y > 0.f ? 1.f : 0.01f;
+                g.z *= rh[j].z > 0.f ? 1.f : 0.01f; g.w *= rh[j].w > 0.f ? 1.f : 0.01f;
+                dg[j] = g;
+            }
+        };
+        if (0 < n_chunks) { load_chunk(0, ra, rg, rh); finish(xa, xg); }
+        if (1 < n_chunks) load_chunk(1, ra, rg, rh);
         for (int ch = 0; ch < n_chunks; ++ch) {
-            if (ch + 1 < n_chunks) load_chunk(ch + 1, ya, yg, yh);   // in flight while chunk ch is stored
+            float4 ya[NAT], yg[NBT];
+            if (ch + 1 < n_chunks) finish(ya, yg);
+            if (ch + 2 < n_chunks) load_chunk(ch + 2, ra, rg, rh);   // in flight for a whole iteration
             const int s = ch % NSTAGE;
             mbar_wait(smem_u32(&sm.empty[s]), ((ch / NSTAGE) & 1) ^ 1);
 #pragma unroll
@@ -469,9 +493,7 @@ fusion_bwd_w_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ 
 #pragma unroll
             for (int j = 0; j < NBT; ++j) {
                 const int task = warp * NBT + j;
-                float4 g = xg[j];
-                g.x *= xh[j].x > 0.f ? 1.f : 0.01f; g.y *= xh[j].y > 0.f ? 1.f : 0.01f;
-                g.z *= xh[j].z > 0.f ? 1.f : 0.01f; g.w *= xh[j].w > 0.f ? 1.f : 0.01f;
+                const float4 g = xg[j];
                 bsum[j] += (g.x + g.y) + (g.z + g.w);
                 const int r = (task % (D / 32)) * 32 + lane, kq = task / (D / 32);
                 const int off = kq * (D / 8) * 32 + (r >> 3) * 32 + (r & 7) * 4;
@@ -483,7 +505,7 @@ fusion_bwd_w_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ 
 #pragma unroll
             for (int j = 0; j < NAT; ++j) xa[j] = ya[j];
 #pragma unroll
-            for (int j = 0; j < NBT; ++j) { xg[j] = yg[j]; xh[j] = yh[j]; }
+            for (int j = 0; j < NBT; ++j) xg[j] = yg[j];
         }
         // bias gradient: once per item slab (feature tile 0 only)
         if (blockIdx.x == 0) {
@@ -491,7 +513,7 @@ fusion_bwd_w_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ 
             for (int j = 0; j < NBT; ++j)
                 atomicAdd(gb + ((warp * NBT + j) % (D / 32)) * 32 + lane, bsum[j]);
         }
-    } else if (warp == LOADER_WARPS) {
+    } else if (warp == BW_LOADERS) {
         // ===== MMA issuer =====
         if (lane == 0) {
             int sub = 0;
@@ -556,7 +578,7 @@ fusion_bwd_w_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == LOADER_WARPS) {
+    if (warp == BW_LOADERS) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
@@ -573,7 +595,7 @@ int launch_bwd_w(const float *Eid, const float *C, const float *H, const float *
     per = (per + KC - 1) / KC * KC;
     slabs = (n_items + per - 1) / per;
     dim3 grid((unsigned)ktiles, (unsigned)slabs);
-    fusion_bwd_w_tc_kernel<D><<<grid, kThreads, sizeof(SmemBw<D>), st>>>(Eid, C, H, gH, n_items, c, per, gW, gb);
+    fusion_bwd_w_tc_kernel<D><<<grid, kBwThreads, sizeof(SmemBw<D>), st>>>(Eid, C, H, gH, n_items, c, per, gW, gb);
     LGCN_LAUNCH_CHECK();
     return 0;
 }

@@ -402,6 +402,38 @@ spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
     int cur = 0;                                          // row (within the chunk) being summed
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
+    // Small graphs (RSEL == 1, L2-resident tables): the walk is INSTRUCTION bound -- ncu r02 at the
+    // Gowalla shape: 65 % issue-active, 47 warp instructions per two-entry step of which 4 FFMA and
+    // 1 LDG, the rest the per-entry row bookkeeping (ballot / shift / popc / compares) and address
+    // selects.  Here every lane prepares ITS entry of a tile once: `meta` = the chunk row the entry
+    // belongs to (the 4 row ends sit in registers; kSkip for slots past the chunk's end) and `goff`
+    // = the gathered row's BYTE offset (small tables: < 2^31; bit 31: the row comes from x_alt); the per-entry
+    // work is then three shuffles, one compare, the load and the FMAs.
+    constexpr bool FAST = RSEL == 1;
+    constexpr int kSkip = 7;
+    [[maybe_unused]] int ends[4] = {INT_MAX, INT_MAX, INT_MAX, INT_MAX};
+    [[maybe_unused]] int meta = kSkip;
+    [[maybe_unused]] unsigned goff = 0u;
+    [[maybe_unused]] const char *xb = reinterpret_cast<const char *>(a.x + sub * 4);        // lane bases
+    [[maybe_unused]] const char *xaltb = reinterpret_cast<const char *>(xalt + sub * 4);
+    [[maybe_unused]] const bool any_alt = altx.n != 0;
+    if constexpr (FAST) {       // opaque: keeps ptxas from re-deriving the lane offset per gather
+        asm volatile("" : "+l"(xb));
+        asm volatile("" : "+l"(xaltb));
+    }
+    if constexpr (FAST) {
+        static_assert(C::R == 4, "the small-graph walk keeps 4 row ends in registers");
+#pragma unroll
+        for (int r = 0; r < 4; ++r) ends[r] = __shfl_sync(0xffffffffu, my_end, r, G::LANES);
+    }
+    [[maybe_unused]] auto prepare_tile = [&](const int2 &c, int t) {
+        const int e = chunk_beg + t + sub;
+        const int row = (e >= ends[0]) + (e >= ends[1]) + (e >= ends[2]) + (e >= ends[3]);
+        meta = (t + sub < n_e) ? row : kSkip;
+        const int cc = c.x & LGCN_COL_MASK;
+        goff = (unsigned)cc * (unsigned)(D * 4) | (altx.has(cc) ? 0x80000000u : 0u);
+    };
+
     // Batches of U gathers issued ahead of the FMAs that consume them.  (A two-deep A/B
     // register pipeline was measured slower: 128 registers -> 16 warps/SM, and ptxas rotated
     // the loads through temporaries.  The gather microbenchmark profiles/micro/gather_bw.cu
@@ -427,6 +459,7 @@ spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
         if (t + G::LANES + sub < n_e) cvn = ld_cv<HINT>(cvp + t + G::LANES + sub, pol);   // next tile, one ahead
         const int cnt = min(n_e - t, G::LANES);           // entries of this tile (may be <= 0)
         const int maxcnt = min(G::LANES, max_n - t);      // warp-uniform
+        if constexpr (FAST) prepare_tile(cv, t);
         for (int j = 0; j < maxcnt; j += U) {
             // Unconditional loads: slots past the end carry col 0 (a valid, cache-resident row).  A
             // predicated 128-bit load makes ptxas stage through 4 temporaries and serialises the
@@ -454,6 +487,25 @@ spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
 #pragma unroll
                     for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
                 }
+            } else if constexpr (FAST) {
+                if (any_alt) {                            // kernel-uniform
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const unsigned o = __shfl_sync(0xffffffffu, goff, j + u, G::LANES);
+                        const float4 *src = reinterpret_cast<const float4 *>(
+                            ((int)o < 0 ? xaltb : xb) + (o & 0x7fffffffu));
+#pragma unroll
+                        for (int v = 0; v < G::VEC; ++v) x[u][v] = __ldg(src + v * G::LANES);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const float4 *src = reinterpret_cast<const float4 *>(
+                            xb + __shfl_sync(0xffffffffu, goff, j + u, G::LANES));
+#pragma unroll
+                        for (int v = 0; v < G::VEC; ++v) x[u][v] = __ldg(src + v * G::LANES);
+                    }
+                }
             } else {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -469,6 +521,35 @@ spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
                         for (int v = 0; v < G::VEC; ++v) x[u][v] = ld_nc_f4(src + v * G::LANES * 4);
                     }
                 }
+            }
+            auto flush_to = [&](int row) {                // store the finished row, zero the empty ones
+#pragma unroll
+                for (int v = 0; v < G::VEC; ++v) {
+                    st_f4(stage + cur * D + sub * 4 + v * G::LANES * 4, acc[v]);
+                    acc[v] = zero4;
+                }
+                for (int r = cur + 1; r < row; ++r)
+#pragma unroll
+                    for (int v = 0; v < G::VEC; ++v)
+                        st_f4(stage + r * D + sub * 4 + v * G::LANES * 4, zero4);
+                cur = row;
+            };
+            if constexpr (FAST) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float wj = __int_as_float(__shfl_sync(0xffffffffu, cv.y, j + u, G::LANES));
+                    const int row = __shfl_sync(0xffffffffu, meta, j + u, G::LANES);
+                    bool take = true;
+                    if (row != cur) {                     // group-uniform; rare
+                        if (row == kSkip) take = false; else flush_to(row);
+                    }
+                    if (take) {
+                        if (XF && xlive[u]) touched |= 1u << row;
+#pragma unroll
+                        for (int v = 0; v < G::VEC; ++v) fma4(acc[v], wj, x[u][v]);
+                    }
+                }
+                continue;
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
