@@ -23,7 +23,10 @@ namespace ftc {
 constexpr int MT = 128;            // items per tile (UMMA M)
 constexpr int KC = 32;             // K chunk (floats) = one 128-byte swizzle-atom row = 4 K=8 instructions
 constexpr int NSTAGE = 3;
-constexpr int LOADER_WARPS = 8;
+#ifndef LGCN_FW_LOADER_WARPS
+#define LGCN_FW_LOADER_WARPS 16    // 8 -> 16: fwd 6.32 -> 6.22 ms, gE_id 3.4 -> 2.2 ms at 4.4 M items (r02_fusion_notes.txt)
+#endif
+constexpr int LOADER_WARPS = LGCN_FW_LOADER_WARPS;
 constexpr int kThreads = (LOADER_WARPS + 1 + 4) * 32;   // loaders, MMA issuer, epilogue
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -167,15 +170,17 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
         // no-swizzle canonical layout (a row's pieces 2 KB apart) they hit the same 4 banks (ncu r02:
         // 396 M conflict wavefronts); in the swizzled layout they write one permuted 128-byte row.
         const int rho = lane >> 3, kap = lane & 7;
-        constexpr int NBT = (D / 8) * 2 / LOADER_WARPS;          // B half-groups (4 rows) per warp
-        static_assert(NBT % 2 == 0, "loader tasks come in pairs");
-        auto a_row = [&](int j) { return (warp * 2 + (j >> 1)) * 8 + (j & 1) * 4 + rho; };
-        auto b_row = [&](int j) { return (warp * (NBT / 2) + (j >> 1)) * 8 + (j & 1) * 4 + rho; };
-        auto load_chunk = [&](int64_t tile, int ch, float4 (&xa)[4], float4 (&xb)[NBT]) {
+        constexpr int NA = (MT / 8) * 2 / LOADER_WARPS;          // A half-groups (4 rows) per warp
+        constexpr int NBT = EID ? (D / 32) * (KC / 4) / LOADER_WARPS  // EID: (k block, o quad) tasks
+                                : (D / 8) * 2 / LOADER_WARPS;         // B half-groups per warp
+        static_assert(NA >= 1 && NBT >= 1, "too many loader warps");
+        auto a_row = [&](int j) { const int t = warp * NA + j; return (t >> 1) * 8 + (t & 1) * 4 + rho; };
+        auto b_row = [&](int j) { const int t = warp * NBT + j; return (t >> 1) * 8 + (t & 1) * 4 + rho; };
+        auto load_chunk = [&](int64_t tile, int ch, float4 (&xa)[NA], float4 (&xb)[NBT]) {
             const int64_t i0 = tile * MT;
             const int k = ch * KC + kap * 4;                     // first float of this lane's piece
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NA; ++j) {
                 const int64_t item = i0 + a_row(j);
                 xa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (item < n_items) {
@@ -212,13 +217,13 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
         // neutral (11.5 -> 11.4 ms): the loaders are not latency bound -- ncu r02 shows the LSU data
         // pipe at 96 % (l1tex__data_pipe_lsu_wavefronts), three quarters of it the wavefronts of these
         // global loads (8 rows x 64 bytes per LDG.128), see profiles/r02_fusion_notes.txt.
-        float4 xa[4], xb[NBT], ya[4], yb[NBT], za[4], zb[NBT];
+        float4 xa[NA], xb[NBT], ya[NA], yb[NBT], za[NA], zb[NBT];
         auto advance = [&](int64_t &t, int &c_) {
             if (++c_ == n_chunks) { c_ = 0; t += gridDim.x; }
         };
         int64_t tile = blockIdx.x, tload = blockIdx.x;            // store cursor / load cursor
         int ch = 0, cload = 0;
-        auto load_next = [&](float4 (&a)[4], float4 (&b)[NBT]) {
+        auto load_next = [&](float4 (&a)[NA], float4 (&b)[NBT]) {
             if (tload < n_tiles) load_chunk(tload, cload, a, b);
             advance(tload, cload);
         };
@@ -226,11 +231,11 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
         load_next(ya, yb);
         load_next(za, zb);
         uint32_t it = 0;
-        auto step = [&](float4 (&a)[4], float4 (&b)[NBT]) {
+        auto step = [&](float4 (&a)[NA], float4 (&b)[NBT]) {
             const int s = it % NSTAGE;
             mbar_wait(smem_u32(&sm.empty[s]), ((it / NSTAGE) & 1) ^ 1);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) store_piece(&sm.A[s][0][0], &sm.A[s][1][0], a_row(j), a[j]);
+            for (int j = 0; j < NA; ++j) store_piece(&sm.A[s][0][0], &sm.A[s][1][0], a_row(j), a[j]);
 #pragma unroll
             for (int j = 0; j < NBT; ++j) {
                 if constexpr (EID) {
