@@ -1,0 +1,4 @@
+// lgcn_spmm_d256.cu -- the SpMM kernels of lgcn_spmm_impl.cuh for 256-float table rows.
+#include "lgcn_spmm_impl.cuh"
+
+LGCN_SPMM_DEFINE_WIDTH(256)

@@ -148,7 +148,7 @@ typedef struct lgcn_spmm_args {
      * other rows the raw tables -- reference models/lightgcn_fusion.py:45-52 builds that table with
      * torch.cat every forward).  Rows c in [alt_begin, alt_begin + alt_rows) are read from
      * x_alt[(c - alt_begin) * d ...] instead of the main table:
-     *   LGCN_SPMM_F_ALT_X       for the gathered rows of x (dense gathers only, no x_rowflag),
+     *   LGCN_SPMM_F_ALT_X       for the gathered rows of x (dense gathers only, no x_rowflag; not ADAM),
      *   LGCN_SPMM_F_ALT_LAYER0  for layers[0] of the MEAN epilogue.
      * NULL / no flag = none. */
     const float   *x_alt;
