@@ -125,7 +125,9 @@ __device__ __forceinline__ AltRange alt_layer0_range(const lgcn_spmm_args &a) {
     if (!ALT) return AltRange{0u, 0u};
     return AltRange{(uint32_t)a.alt_begin, (a.flags & LGCN_SPMM_F_ALT_LAYER0) ? (uint32_t)a.alt_rows : 0u};
 }
+template <bool ALT>      // ADAM instantiations: ALT = "the call carries g_skip" (2 % of a plain ADAM hop)
 __device__ __forceinline__ AltRange adam_skip_range(const lgcn_spmm_args &a) {
+    if (!ALT) return AltRange{0u, 0u};
     return AltRange{(uint32_t)a.skip_begin, a.g_skip ? (uint32_t)a.skip_rows : 0u};
 }
 template <int D>
@@ -191,7 +193,7 @@ __device__ __forceinline__ void epilogue_row(const lgcn_spmm_args &a, int64_t ro
         } else {  // LGCN_SPMM_ADAM
             float4 g = acc[v];
             if (a.addend) { const float4 t = ld_stream_f4(a.addend + off); add4(g, t); }
-            if (adam_skip_range(a).has((int)row)) {      // not a parameter row: hand the gradient on
+            if (adam_skip_range<ALT>(a).has((int)row)) {      // not a parameter row: hand the gradient on
                 st_f4(a.g_skip - (size_t)a.skip_begin * D + off, g);
                 continue;
             }
@@ -240,7 +242,7 @@ __device__ __forceinline__ void chunk_epilogue(const lgcn_spmm_args &a, const fl
                 on[i] = rr < nvr && !((long_bits >> rr) & 1u) && ((wmask >> rr) & 1u);
                 off[i] = (size_t)(r0 + rr) * D + coff;
             }
-            [[maybe_unused]] const AltRange alt0 = alt_layer0_range<ALT>(a), skip = adam_skip_range(a);
+            [[maybe_unused]] const AltRange alt0 = alt_layer0_range<ALT>(a), skip = adam_skip_range<ALT>(a);
             if (MODE == LGCN_SPMM_PLAIN) {
 #pragma unroll
                 for (int i = 0; i < B; ++i)
@@ -1201,7 +1203,8 @@ static bool ring_path(bool small, int mode, int32_t flags) {
 }
 
 // ALT: the call reads rows from x_alt (LGCN_SPMM_F_ALT_X / ALT_LAYER0; lgcn_spmm() admits the flags
-// for PLAIN, dense ADD and MEAN only) -- its own instantiations, so that every other call pays nothing.
+// for PLAIN, dense ADD and MEAN only) or, in ADAM mode, carries g_skip -- its own instantiations, so
+// that every other call pays nothing.
 template <int D, int MODE, bool ALT>
 static int launch_mode_alt(const lgcn_spmm_args &a, cudaStream_t st) {
     using G = RowGeom<D>;
@@ -1242,6 +1245,8 @@ template <int D, int MODE>
 static int launch_mode(const lgcn_spmm_args &a, cudaStream_t st) {
     if constexpr (MODE != LGCN_SPMM_ADAM) {
         if (a.flags & (LGCN_SPMM_F_ALT_X | LGCN_SPMM_F_ALT_LAYER0)) return launch_mode_alt<D, MODE, true>(a, st);
+    } else {
+        if (a.g_skip) return launch_mode_alt<D, MODE, true>(a, st);
     }
     return launch_mode_alt<D, MODE, false>(a, st);
 }

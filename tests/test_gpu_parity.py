@@ -812,7 +812,10 @@ def test_feature_sharded_fusion_step_emulated_on_one_gpu(golden, dev):
         fus = dict(content=C[r * ipr:min(I, (r + 1) * ipr)].contiguous(),
                    weight=_t(g["init/item_fusion_layer.weight"], dev),
                    bias=_t(g["init/item_fusion_layer.bias"], dev), alltoall=make_alltoall(r))
-        engs.append(FeatureShardedEngine(csr, U, I, B, K, column_shard(full, r, world), world=world, rank=r,
+        # one graph object per rank, as in one process per GPU: a NormAdjCSR owns the long-row
+        # segment workspace of its lgcn_spmm calls, which two host threads must not share
+        engs.append(FeatureShardedEngine(csr if r == 0 else _graph(g, dev), U, I, B, K,
+                                         column_shard(full, r, world), world=world, rank=r,
                                          allreduce=make_allreduce(r), fusion=fus, lr=float(g["lr"]),
                                          weight_decay=float(g["lam"]), batch_size=int(g["bs"])))
     losses = [[], []]
