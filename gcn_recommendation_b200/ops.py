@@ -73,7 +73,7 @@ class _timed:
 
 def _spmm_plan(n_rows, d, n_long):
     """(kernel launches per ``lgcn_spmm`` call, small-graph path?) as the library itself decides
-    (host-only query, csrc/lgcn_spmm.cu ``launch_mode``)."""
+    (host-only query, csrc/lgcn_spmm_impl.cuh ``launch_mode``)."""
     small = ctypes.c_int32(0)
     n = _lib.load().lgcn_spmm_launches(int(n_rows), int(d), int(n_long), int(SPMM_FLAGS_EXTRA),
                                        ctypes.byref(small))
@@ -129,7 +129,7 @@ def _spmm_args(g, x, mode, d):
 
 def spmm_kernel_name(g, d, mode, sparse_x=False):
     """Name of the main kernel ``lgcn_spmm`` picks for this graph / width / mode (host-only query
-    of the library's own selection, csrc/lgcn_spmm.cu ``launch_mode``; bench.py labels the
+    of the library's own selection, csrc/lgcn_spmm_impl.cuh ``launch_mode``; bench.py labels the
     roofline with it)."""
     code = {"plain": SPMM_PLAIN, "add": SPMM_ADD, "add_xs": SPMM_ADD, "add_xf": SPMM_ADD,
             "mean": SPMM_MEAN, "adam": SPMM_ADAM}[mode]
