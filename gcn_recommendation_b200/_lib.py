@@ -24,8 +24,9 @@ SPMM_F_FORCE_RING = 16
 SPMM_F_NO_PREFETCH = 32
 SPMM_F_ALT_X = 64
 SPMM_F_ALT_LAYER0 = 128
+SPMM_F_LONG_DONE = 256
 BPR_GP_INCLUDES_GF, BPR_NO_GRAD = 1, 2
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class SpmmArgs(ctypes.Structure):
@@ -42,6 +43,7 @@ class SpmmArgs(ctypes.Structure):
         ("y_rowflag", c_vp),
         ("x_alt", c_vp), ("alt_begin", c_i64), ("alt_rows", c_i64),
         ("g_skip", c_vp), ("skip_begin", c_i64), ("skip_rows", c_i64),
+        ("chunk_order", c_vp), ("long_done", c_vp),
     ]
 
 

@@ -101,5 +101,6 @@ extern "C" int lgcn_spmm_launches(int64_t n_rows, int32_t d, int32_t n_long, int
     const bool small = small_for_dim(n_rows, d, flags);
     if (small_path) *small_path = small ? 1 : 0;
     if (n_long == 0) return 1;                 // main kernel only
-    return small ? 2 : 3;                      // (+ segments) + combine
+    if (small) return (flags & LGCN_SPMM_F_LONG_DONE) ? 1 : 2;   // segments ride in the main launch (+ combine)
+    return 3;                                  // segments + main + combine
 }

@@ -343,8 +343,10 @@ __device__ __forceinline__ unsigned sparse_out_mask(const lgcn_spmm_args &a, con
     return wmask;
 }
 
-template <int D, bool ALT>
+template <int D, bool ALT, int FMODE = -1>
 __device__ __forceinline__ void long_seg_body(const lgcn_spmm_args &a, int64_t block);
+template <int D, int MODE, bool ALT, int CBMAX>
+__device__ __forceinline__ void combine_long_row(const lgcn_spmm_args &a, int i, int sub);
 
 // ---- main kernel: one worker per chunk of R rows ---------------------------------------------
 template <int D, int MODE, int RSEL, bool HINT, bool XF, bool ALT>
@@ -353,13 +355,16 @@ __global__ void __launch_bounds__(kThreads, RSEL == 1 ? (MODE == LGCN_SPMM_MEAN 
 spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
     using G = RowGeom<D>;
     using C = ChunkCfg<D, RSEL>;
+    [[maybe_unused]] const int64_t seg_blocks =
+        (RSEL == 1 && a.n_long > 0) ? (a.n_seg + kWarps * G::GROUPS - 1) / (kWarps * G::GROUPS) : 0;
     if constexpr (RSEL == 1) {
         // small (L2-resident, latency-bound) graphs: the long-row segment workers ride in the same
         // launch as extra CTAs, so the two independent phases overlap (Gowalla shape: the separate
         // 31 us segment launch was a quarter of an SpMM call)
-        const int64_t cb = (a.n_rows + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
-        if ((int64_t)blockIdx.x >= cb) {
-            long_seg_body<D, ALT>(a, (int64_t)blockIdx.x - cb);
+        // They take the FIRST blocks of the grid: 128-entry segments are the longest work items, and
+        // with long_done the rows they finish are combined while the chunk workers still run.
+        if ((int64_t)blockIdx.x < seg_blocks) {
+            long_seg_body<D, ALT, MODE>(a, (int64_t)blockIdx.x);
             return;
         }
     }
@@ -374,8 +379,12 @@ spmm_chunk_kernel(const __grid_constant__ lgcn_spmm_args a) {
     const unsigned gbits = (G::LANES == 32) ? 0xffffffffu : ((1u << G::LANES) - 1u);
     float *stage = stage_all + (size_t)((warp * G::GROUPS + grp) * C::R) * D;
 
-    const int64_t worker = ((int64_t)blockIdx.x * kWarps + warp) * G::GROUPS + grp;
-    const int64_t r0 = worker * C::R;
+    const int64_t worker = (((int64_t)blockIdx.x - seg_blocks) * kWarps + warp) * G::GROUPS + grp;
+    int64_t chunk = worker;
+    if constexpr (RSEL == 1) {      // optional plan: chunks in descending length (equal lengths share a warp)
+        if (a.chunk_order && worker * C::R < a.n_rows) chunk = __ldg(a.chunk_order + worker);
+    }
+    const int64_t r0 = chunk * C::R;
     const int64_t left = a.n_rows - r0;
     const int nvr = left <= 0 ? 0 : (left < C::R ? (int)left : C::R);
 
@@ -994,7 +1003,10 @@ spmm_live_kernel(const __grid_constant__ lgcn_spmm_args a) {
 }
 
 // ---- long rows: one worker per segment, partial sums to seg_ws -----------------------------
-template <int D, bool ALT>
+// FMODE >= 0 (small graphs, inside the chunk kernel's launch, lgcn_spmm_args.long_done given): the
+// worker that delivers the LAST partial of a long row also combines the row and runs its epilogue
+// in mode FMODE -- fence, count, fence: the classic last-arriver hand-over, no waiting anywhere.
+template <int D, bool ALT, int FMODE>
 __device__ __forceinline__ void long_seg_body(const lgcn_spmm_args &a, int64_t block) {
     using G = RowGeom<D>;
     const int lane = threadIdx.x & 31;
@@ -1003,12 +1015,14 @@ __device__ __forceinline__ void long_seg_body(const lgcn_spmm_args &a, int64_t b
     const int64_t warp = block * kWarps + (threadIdx.x >> 5);
     const int64_t seg = warp * G::GROUPS + grp;
     int beg = 0, deg = 0;
+    [[maybe_unused]] int long_i = 0;                      // the long row this segment belongs to
     if (seg < a.n_seg) {
         int lo = 0, hi = a.n_long;                        // last i with long_seg_ptr[i] <= seg
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
             if (__ldg(a.long_seg_ptr + mid) <= seg) lo = mid; else hi = mid;
         }
+        long_i = lo;
         const int rbeg = __ldg(a.long_rowptr + lo), rend = __ldg(a.long_rowptr + lo + 1);
         beg = rbeg + (int)(seg - __ldg(a.long_seg_ptr + lo)) * a.seg_len;
         deg = min(a.seg_len, rend - beg);
@@ -1097,6 +1111,21 @@ __device__ __forceinline__ void long_seg_body(const lgcn_spmm_args &a, int64_t b
         for (int v = 0; v < G::VEC; ++v)
             st_f4(a.seg_ws + (size_t)seg * D + sub * 4 + v * G::LANES * 4, acc[v]);
     }
+    if constexpr (FMODE >= 0) {
+        if (a.long_done) {                                // kernel-uniform
+            if (seg < a.n_seg) __threadfence();           // my part of the partial is visible device-wide
+            __syncwarp();
+            int old = -2;
+            if (seg < a.n_seg && sub == 0) old = atomicAdd(a.long_done + long_i, 1);
+            old = __shfl_sync(0xffffffffu, old, 0, G::LANES);
+            if (seg < a.n_seg &&
+                old + 1 == __ldg(a.long_seg_ptr + long_i + 1) - __ldg(a.long_seg_ptr + long_i)) {
+                __threadfence();                          // the other workers' partials, after their counts
+                combine_long_row<D, FMODE, ALT, 8 / RowGeom<D>::VEC>(a, long_i, sub);
+                if (sub == 0) a.long_done[long_i] = 0;    // re-armed for the next call
+            }
+        }
+    }
 }
 
 template <int D, bool ALT>
@@ -1105,23 +1134,18 @@ __global__ void __launch_bounds__(kThreads) spmm_long_seg_kernel(const __grid_co
 }
 
 // ---- long rows: combine the segment partials in order, then the epilogue -------------------
-template <int D, int MODE, bool ALT>
-__global__ void __launch_bounds__(kThreads) spmm_long_combine_kernel(const __grid_constant__ lgcn_spmm_args a) {
+// (partials come from other SMs: L2 loads, never a stale L1 line)
+template <int D, int MODE, bool ALT, int CBMAX>      // CBMAX: partial loads in flight (8 inside the 64-register chunk kernel)
+__device__ __forceinline__ void combine_long_row(const lgcn_spmm_args &a, int i, int sub) {
     using G = RowGeom<D>;
-    const int lane = threadIdx.x & 31;
-    const int grp = lane / G::LANES;
-    const int sub = lane % G::LANES;
-    const int64_t warp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
-    const int64_t i = warp * G::GROUPS + grp;
-    if (i >= a.n_long) return;
     const int s0 = __ldg(a.long_seg_ptr + i), s1 = __ldg(a.long_seg_ptr + i + 1);
     float4 acc[G::VEC];
 #pragma unroll
     for (int v = 0; v < G::VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     // partials are summed in segment order; loads are issued CB segments ahead of the adds and are
     // unconditional (clamped index): the hottest row's chain of dependent batches is the whole
-    // duration of this kernel on small graphs (Gowalla shape: ~300 segments)
-    constexpr int CB = G::VEC > 1 ? 8 : 16;
+    // duration of a separate combine launch on small graphs (Gowalla shape: ~300 segments)
+    constexpr int CB = (G::VEC > 1 ? 8 : 16) < CBMAX ? (G::VEC > 1 ? 8 : 16) : CBMAX;
     for (int s = s0; s < s1; s += CB) {
         float4 t[CB][G::VEC];
 #pragma unroll
@@ -1129,8 +1153,8 @@ __global__ void __launch_bounds__(kThreads) spmm_long_combine_kernel(const __gri
             const int sk = min(s + k, s1 - 1);
 #pragma unroll
             for (int v = 0; v < G::VEC; ++v)
-                t[k][v] = *reinterpret_cast<const float4 *>(a.seg_ws + (size_t)sk * D + sub * 4 +
-                                                             v * G::LANES * 4);
+                t[k][v] = __ldcg(reinterpret_cast<const float4 *>(a.seg_ws + (size_t)sk * D + sub * 4 +
+                                                                  v * G::LANES * 4));
         }
 #pragma unroll
         for (int k = 0; k < CB; ++k)
@@ -1142,6 +1166,16 @@ __global__ void __launch_bounds__(kThreads) spmm_long_combine_kernel(const __gri
             }
     }
     epilogue_row<D, MODE, ALT>(a, __ldg(a.long_row_ids + i), acc);
+}
+
+template <int D, int MODE, bool ALT>
+__global__ void __launch_bounds__(kThreads) spmm_long_combine_kernel(const __grid_constant__ lgcn_spmm_args a) {
+    using G = RowGeom<D>;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const int64_t i = warp * G::GROUPS + lane / G::LANES;
+    if (i >= a.n_long) return;
+    combine_long_row<D, MODE, ALT, 16>(a, (int)i, lane % G::LANES);
 }
 
 template <int D, int MODE, int RSEL, bool HINT, bool XF, bool ALT>
@@ -1233,7 +1267,7 @@ static int launch_mode_alt(const lgcn_spmm_args &a, cudaStream_t st) {
         else rc = launch_chunks<D, MODE, 0, false, false, ALT>(a, st);
         if (rc) return rc;
     }
-    if (a.n_long > 0) {
+    if (a.n_long > 0 && !(small && a.n_rows > 0 && a.long_done)) {   // small + long_done: combined in place
         const unsigned gc = (unsigned)((a.n_long + groups_per_block - 1) / groups_per_block);
         spmm_long_combine_kernel<D, MODE, ALT><<<gc, kThreads, 0, st>>>(a);
         LGCN_LAUNCH_CHECK();

@@ -23,6 +23,10 @@ LONG_ROW_THRESHOLD_LARGE = 512
 SEG_LEN_LARGE = 512
 SMALL_GRAPH_ROWS = 1_000_000
 TINY_GRAPH_ROWS = 8192
+# graphs up to this many rows get the small-graph plan (chunk order, long-row counters); whether the
+# small-graph kernels actually run is the library's decision (lgcn_spmm_launches), the plan is
+# 4 bytes per 4 rows
+SMALL_PLAN_MAX_ROWS = 1 << 20
 
 
 class NormAdjCSR:
@@ -77,10 +81,12 @@ class NormAdjCSR:
         deg = np.diff(rp.astype(np.int64))
         long_ids = (np.nonzero(deg > threshold)[0] if threshold > 0 else np.zeros(0, np.int64))
         packed = torch.stack([self.col, self.val.view(torch.int32)], dim=1)     # [nnz, 2] int32
+        self.chunk_order = self.long_done = None
         if len(long_ids) == 0:
             self.long_row_threshold = 0 if threshold <= 0 else self.long_row_threshold
             self.rowptr_flagged = self.rowptr
             self.colval = packed.contiguous()
+            self._plan_small_graph(deg)
             return
         is_long = np.zeros(self.n_rows, bool)
         is_long[long_ids] = True
@@ -106,6 +112,24 @@ class NormAdjCSR:
         self.long_row_ids = torch.from_numpy(long_ids.astype(np.int32)).to(dev)
         self.long_rowptr = torch.from_numpy(long_rp).to(dev)
         self.long_seg_ptr = torch.from_numpy(seg_ptr).to(dev)
+        self._plan_small_graph(short_deg)
+
+    def _plan_small_graph(self, short_deg):
+        """Plan of the small-graph (L2-resident) kernels, include/lgcn.h ``chunk_order`` /
+        ``long_done``: the 4-row chunks in descending order of their entry count -- a warp's two
+        (or more) workers then walk chunks of equal length instead of idling to the longer one,
+        and the longest work is scheduled first -- and one counter per long row, so that the
+        worker delivering a row's last segment combines it and no combine launch is needed.
+        Results do not depend on either (tests run with and without: ``LGCN_NO_SMALL_PLAN=1``)."""
+        if self.n_rows > SMALL_PLAN_MAX_ROWS or os.environ.get("LGCN_NO_SMALL_PLAN"):
+            return
+        n_chunks = (self.n_rows + 3) // 4
+        per_chunk = np.zeros(n_chunks * 4, np.int64)
+        per_chunk[:self.n_rows] = short_deg
+        order = np.argsort(-per_chunk.reshape(n_chunks, 4).sum(1), kind="stable").astype(np.int32)
+        self.chunk_order = torch.from_numpy(order).to(self.device)
+        if self.n_long > 0:
+            self.long_done = torch.zeros(self.n_long, dtype=torch.int32, device=self.device)
 
     # ---- L2 residency classes of the gathered columns (include/lgcn.h, LGCN_COL_*) ----------
     def mark_hot_columns(self, n_hot, col_degree=None):

@@ -71,12 +71,13 @@ class _timed:
         return False
 
 
-def _spmm_plan(n_rows, d, n_long):
+def _spmm_plan(n_rows, d, n_long, long_done=False):
     """(kernel launches per ``lgcn_spmm`` call, small-graph path?) as the library itself decides
-    (host-only query, csrc/lgcn_spmm_impl.cuh ``launch_mode``)."""
+    (host-only query, csrc/lgcn_spmm_impl.cuh ``launch_mode``).  ``long_done``: the calls carry
+    the graph's long-row counters (small graphs then combine long rows inside the main launch)."""
     small = ctypes.c_int32(0)
-    n = _lib.load().lgcn_spmm_launches(int(n_rows), int(d), int(n_long), int(SPMM_FLAGS_EXTRA),
-                                       ctypes.byref(small))
+    flags = int(SPMM_FLAGS_EXTRA) | (_lib.SPMM_F_LONG_DONE if long_done else 0)
+    n = _lib.load().lgcn_spmm_launches(int(n_rows), int(d), int(n_long), flags, ctypes.byref(small))
     if n <= 0:
         check(n)
     return n, bool(small.value)
@@ -88,7 +89,7 @@ def _small_graph(n_rows, d):
 
 def spmm_launches(g, d):
     """Kernels one ``lgcn_spmm`` call launches for this graph / width."""
-    return _spmm_plan(g.n_rows, d, g.n_long)[0]
+    return _spmm_plan(g.n_rows, d, g.n_long, getattr(g, "long_done", None) is not None)[0]
 
 
 def _launch_spmm(a, g, dev, tag):
@@ -124,6 +125,8 @@ def _spmm_args(g, x, mode, d):
         a.long_seg_ptr = ptr(g.long_seg_ptr, "i32")
         a.seg_len, a.n_seg = g.seg_len, g.n_seg
         a.seg_ws = ptr(g.seg_ws(d))
+        a.long_done = ptr(getattr(g, "long_done", None), "i32", allow_none=True)
+    a.chunk_order = ptr(getattr(g, "chunk_order", None), "i32", allow_none=True)
     return a
 
 

@@ -33,7 +33,7 @@ typedef struct CUstream_st *lgcn_stream_t; /* == cudaStream_t */
 #define LGCN_API
 #endif
 
-#define LGCN_ABI_VERSION 6
+#define LGCN_ABI_VERSION 7
 
 #define LGCN_E_BAD_DIM   (-1) /* embedding dim not supported              */
 #define LGCN_E_BAD_ARG   (-2) /* null pointer / negative size / bad mode  */
@@ -158,6 +158,16 @@ typedef struct lgcn_spmm_args {
      * not added) is stored to g_skip[(r - skip_begin) * d ...] for the projection's backward. */
     float         *g_skip;
     int64_t        skip_begin, skip_rows;
+    /* Small (L2-resident) graphs only -- ignored on the large-graph path; both optional (NULL).
+     * chunk_order: a permutation of the ceil(n_rows / 4) four-row chunks; worker w takes chunk
+     *   chunk_order[w].  Sorted by descending entry count it pairs chunks of equal length in a warp
+     *   and schedules the longest work first.  Results do not depend on it.
+     * long_done: n_long zero-initialised counters.  When given, the worker that stores the LAST
+     *   segment partial of a long row combines the row's partials (in segment order, as the combine
+     *   launch would) and runs its epilogue, then re-arms the counter: no separate combine launch.
+     *   One concurrent lgcn_spmm call per counter array. */
+    const int32_t *chunk_order;
+    int32_t       *long_done;
 } lgcn_spmm_args;
 
 /* tables do not fit L2: stream entries / outputs / epilogue operands with L2 evict_first so
@@ -169,6 +179,7 @@ typedef struct lgcn_spmm_args {
 #define LGCN_SPMM_F_COLD_FIRST 8    /* gathers of unclassified columns use evict_first too   */
 #define LGCN_SPMM_F_FORCE_RING 16   /* (no-op since ABI v5: the ring kernel serves ADAM too)  */
 #define LGCN_SPMM_F_NO_PREFETCH 32  /* no L2 prefetch of the epilogue operands (A/B only)    */
+#define LGCN_SPMM_F_LONG_DONE 256   /* lgcn_spmm_launches() only: the call will pass long_done */
 #define LGCN_SPMM_F_ALT_X 64        /* gathers of rows in the alt range read x_alt           */
 #define LGCN_SPMM_F_ALT_LAYER0 128  /* MEAN: layers[0] rows in the alt range read x_alt      */
 

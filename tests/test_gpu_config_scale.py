@@ -267,3 +267,44 @@ def test_device_csr_build_matches_host_build_at_gowalla_shape(gowalla, dev):
     assert np.array_equal(digest(devb.val.cpu().numpy()), g["adj_val_digest"])
     assert torch.equal(host.colval, devb.colval) and torch.equal(host.rowptr_flagged, devb.rowptr_flagged)
     assert host.n_long == devb.n_long and host.n_seg == devb.n_seg
+
+
+def test_small_graph_plan_is_result_neutral_at_gowalla_shape(gowalla, dev, monkeypatch):
+    """The small-graph plan (include/lgcn.h ``chunk_order`` / ``long_done``: chunks walked in
+    descending length, long rows combined by the worker that delivers their last segment) must not
+    change a single bit in any mode, must leave the counters re-armed, and saves the combine launch."""
+    from gcn_recommendation_b200 import ops
+    from gcn_recommendation_b200.graph import NormAdjCSR
+    g, inter, tu, ti, vu, vi = gowalla
+    U, I, B = inter.num_users, inter.num_items, inter.num_brands
+    planned = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev)
+    monkeypatch.setenv("LGCN_NO_SMALL_PLAN", "1")
+    plain = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev)
+    monkeypatch.delenv("LGCN_NO_SMALL_PLAN")
+    assert planned.chunk_order is not None and planned.long_done is not None and planned.n_long > 0
+    assert plain.chunk_order is None and plain.long_done is None
+    order = planned.chunk_order.cpu().numpy()
+    assert np.array_equal(np.sort(order), np.arange((planned.n_rows + 3) // 4))
+    N = planned.n_rows
+    gen = torch.Generator(device=dev).manual_seed(7)
+    for d in (64, 16, 128):
+        assert ops.spmm_launches(planned, d) == 1 and ops.spmm_launches(plain, d) == 2
+        x = torch.randn((N, d), device=dev, generator=gen)
+        a1 = torch.randn((N, d), device=dev, generator=gen)
+        for _ in range(2):                                   # the second pass runs on re-armed counters
+            y0, y1 = ops.spmm(plain, x), ops.spmm(planned, x)
+            assert torch.equal(y0, y1)
+            assert torch.equal(ops.spmm(plain, x, addend=a1), ops.spmm(planned, x, addend=a1))
+            assert torch.equal(ops.spmm(plain, y0, mean_layers=[x, y0]), ops.spmm(planned, y0, mean_layers=[x, y0]))
+            assert int(planned.long_done.abs().sum()) == 0
+        sc = torch.zeros(4, device=dev)
+        step = torch.zeros(1, dtype=torch.int64, device=dev)
+        ops.adam_tick(step, sc, 1e-3, (0.9, 0.999))
+        outs = []
+        for gr in (plain, planned):
+            p, m, v = a1.clone(), torch.zeros_like(a1), torch.zeros_like(a1)
+            ops.spmm_adam(gr, x, p, m, v, sc, addend=a1)
+            outs.append((p, m, v))
+        for t0, t1 in zip(*outs):
+            assert torch.equal(t0, t1)
+        assert int(planned.long_done.abs().sum()) == 0

@@ -35,6 +35,8 @@ def test_spmm_plan_query_matches_documented_selection():
     from gcn_recommendation_b200 import _lib, ops
     assert ops._spmm_plan(70_840, 64, 0) == (1, True)
     assert ops._spmm_plan(70_840, 64, 1600) == (2, True)
+    assert ops._spmm_plan(70_840, 64, 1600, long_done=True) == (1, True)      # combined in place
+    assert ops._spmm_plan(14_700_001, 64, 2749, long_done=True) == (3, False)
     for d in (16, 32, 64, 128):
         assert ops._spmm_plan(14_700_001, d, 2749) == (3, False)
     old = ops.SPMM_FLAGS_EXTRA
