@@ -55,6 +55,7 @@ _SIGNATURES = {
     "lgcn_edge_weights": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "lgcn_spmm": (ctypes.c_int, [ctypes.POINTER(SpmmArgs), c_vp]),
     "lgcn_sizeof_spmm_args": (ctypes.c_size_t, []),
+    "lgcn_spmm_chunk_rows": (ctypes.c_int, [c_i64, c_i32, c_i32]),
     "lgcn_spmm_launches": (ctypes.c_int, [c_i64, c_i32, c_i32, c_i32, ctypes.POINTER(ctypes.c_int32)]),
     "lgcn_spmm_kernel_name": (ctypes.c_int, [c_i64, c_i32, c_i32, c_i32, c_i32, ctypes.c_char_p,
                                              ctypes.c_size_t]),

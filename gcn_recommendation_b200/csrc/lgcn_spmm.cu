@@ -93,6 +93,19 @@ extern "C" int lgcn_spmm_kernel_name(int64_t n_rows, int32_t d, int32_t mode, in
     return 0;
 }
 
+extern "C" int lgcn_spmm_chunk_rows(int64_t n_rows, int32_t d, int32_t flags) {
+    using namespace lgcn;
+    if (n_rows < 0) return LGCN_E_BAD_ARG;
+    switch (d) {
+        case 16:  return order_chunk_rows<16>(n_rows, flags);
+        case 32:  return order_chunk_rows<32>(n_rows, flags);
+        case 64:  return order_chunk_rows<64>(n_rows, flags);
+        case 128: return order_chunk_rows<128>(n_rows, flags);
+        case 256: return order_chunk_rows<256>(n_rows, flags);
+    }
+    return LGCN_E_BAD_DIM;
+}
+
 extern "C" int lgcn_spmm_launches(int64_t n_rows, int32_t d, int32_t n_long, int32_t flags,
                                   int32_t *small_path) {
     using namespace lgcn;

@@ -716,7 +716,9 @@ spmm_ring_kernel(const __grid_constant__ lgcn_spmm_args a) {
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
 
     const int64_t worker = ((int64_t)blockIdx.x * kRingWarps + warp) * G::GROUPS + grp;
-    const int64_t r0 = worker * C::R;
+    int64_t chunk = worker;         // optional plan: chunks of similar length share a warp (GROUPS > 1)
+    if (G::GROUPS > 1 && a.chunk_order && worker * C::R < a.n_rows) chunk = __ldg(a.chunk_order + worker);
+    const int64_t r0 = chunk * C::R;
     const int64_t left = a.n_rows - r0;
     const int nvr = left <= 0 ? 0 : (left < C::R ? (int)left : C::R);
 
@@ -883,7 +885,9 @@ spmm_live_kernel(const __grid_constant__ lgcn_spmm_args a) {
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
 
     const int64_t worker = ((int64_t)blockIdx.x * kRingWarps + warp) * G::GROUPS + grp;
-    const int64_t r0 = worker * C::R;
+    int64_t chunk = worker;         // optional plan: chunks of similar length share a warp (GROUPS > 1)
+    if (G::GROUPS > 1 && a.chunk_order && worker * C::R < a.n_rows) chunk = __ldg(a.chunk_order + worker);
+    const int64_t r0 = chunk * C::R;
     const int64_t left = a.n_rows - r0;
     const int nvr = left <= 0 ? 0 : (left < C::R ? (int)left : C::R);
 
@@ -1224,6 +1228,15 @@ template <int D>
 static bool small_graph(int64_t n_rows, int32_t flags) {
     const int64_t big_workers = n_rows / ChunkCfg<D, 0>::R;
     return big_workers < (int64_t)kNumSMs * 32 * RowGeom<D>::GROUPS && !(flags & LGCN_SPMM_F_BIG_PATH);
+}
+
+// Rows per chunk of the main kernel lgcn_spmm will run, when that kernel follows chunk_order (0 = it
+// does not: one worker per warp, or the register-batch chunk kernel of the large-graph path).
+template <int D>
+static int order_chunk_rows(int64_t n_rows, int32_t flags) {
+    if (small_graph<D>(n_rows, flags)) return 4;
+    if (flags & LGCN_SPMM_F_NO_RING) return 0;
+    return RowGeom<D>::GROUPS > 1 ? RingCfg<D>::R : 0;      // ring and live kernels: same chunks
 }
 
 // Large graphs: the cp.async ring kernel for every epilogue; the flagged (sparse-input) hops run

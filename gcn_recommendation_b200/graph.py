@@ -27,6 +27,7 @@ TINY_GRAPH_ROWS = 8192
 # small-graph kernels actually run is the library's decision (lgcn_spmm_launches), the plan is
 # 4 bytes per 4 rows
 SMALL_PLAN_MAX_ROWS = 1 << 20
+CHUNK_ORDER_WINDOW = 2048      # chunks per sorting window on large graphs (4-8 rows each)
 
 
 class NormAdjCSR:
@@ -81,7 +82,8 @@ class NormAdjCSR:
         deg = np.diff(rp.astype(np.int64))
         long_ids = (np.nonzero(deg > threshold)[0] if threshold > 0 else np.zeros(0, np.int64))
         packed = torch.stack([self.col, self.val.view(torch.int32)], dim=1)     # [nnz, 2] int32
-        self.chunk_order = self.long_done = None
+        self.long_done = None
+        self._chunk_orders = {}
         if len(long_ids) == 0:
             self.long_row_threshold = 0 if threshold <= 0 else self.long_row_threshold
             self.rowptr_flagged = self.rowptr
@@ -114,22 +116,48 @@ class NormAdjCSR:
         self.long_seg_ptr = torch.from_numpy(seg_ptr).to(dev)
         self._plan_small_graph(short_deg)
 
-    def _plan_small_graph(self, short_deg):
-        """Plan of the small-graph (L2-resident) kernels, include/lgcn.h ``chunk_order`` /
-        ``long_done``: the 4-row chunks in descending order of their entry count -- a warp's two
-        (or more) workers then walk chunks of equal length instead of idling to the longer one,
-        and the longest work is scheduled first -- and one counter per long row, so that the
-        worker delivering a row's last segment combines it and no combine launch is needed.
-        Results do not depend on either (tests run with and without: ``LGCN_NO_SMALL_PLAN=1``)."""
-        if self.n_rows > SMALL_PLAN_MAX_ROWS or os.environ.get("LGCN_NO_SMALL_PLAN"):
+    def _plan_small_graph(self, short_deg=None):
+        """Long-row counters of the small-graph (L2-resident) kernels, include/lgcn.h ``long_done``:
+        the worker delivering a long row's last segment combines it, no combine launch is needed.
+        Results do not depend on it (tests run with and without: ``LGCN_NO_SMALL_PLAN=1``)."""
+        self._chunk_orders = {}
+        plan = not os.environ.get("LGCN_NO_SMALL_PLAN")            # decided when the graph is built
+        self._order_enabled = plan and not os.environ.get("LGCN_NO_CHUNK_ORDER")
+        if self.n_rows > SMALL_PLAN_MAX_ROWS or not plan:
             return
-        n_chunks = (self.n_rows + 3) // 4
-        per_chunk = np.zeros(n_chunks * 4, np.int64)
-        per_chunk[:self.n_rows] = short_deg
-        order = np.argsort(-per_chunk.reshape(n_chunks, 4).sum(1), kind="stable").astype(np.int32)
-        self.chunk_order = torch.from_numpy(order).to(self.device)
         if self.n_long > 0:
             self.long_done = torch.zeros(self.n_long, dtype=torch.int32, device=self.device)
+
+    def chunk_order_for(self, rows_per_chunk, windowed):
+        """``lgcn_spmm_args.chunk_order`` for chunks of ``rows_per_chunk`` rows (include/lgcn.h):
+        chunks of similar entry count next to each other, so that the workers sharing a warp (tables
+        narrower than 128 floats) walk equally long streams.  Small graphs: one global descending
+        sort (longest work first).  Large graphs (``windowed``): descending inside windows of
+        CHUNK_ORDER_WINDOW chunks, so that entries, outputs and epilogue operands still stream
+        through HBM window by window.  Pure device integer work, once per (graph, chunk size)."""
+        if not getattr(self, "_order_enabled", False):
+            return None
+        key = (int(rows_per_chunk), bool(windowed))
+        orders = self.__dict__.setdefault("_chunk_orders", {})
+        if key not in orders:
+            R = key[0]
+            rp = self.rowptr_flagged.to(torch.int64) & 0x7fffffff       # short-row prefix sums
+            n_chunks = (self.n_rows + R - 1) // R
+            deg = torch.zeros(n_chunks * R, dtype=torch.int64, device=self.device)
+            deg[:self.n_rows] = rp[1:] - rp[:-1]
+            lens = deg.view(n_chunks, R).sum(1)
+            if not windowed:
+                order = torch.sort(lens, descending=True, stable=True).indices
+            else:
+                W = int(os.environ.get("LGCN_CHUNK_ORDER_WINDOW", CHUNK_ORDER_WINDOW))
+                n_win = (n_chunks + W - 1) // W
+                padded = torch.full((n_win * W,), -1, dtype=torch.int64, device=self.device)
+                padded[:n_chunks] = lens
+                idx = torch.sort(padded.view(n_win, W), dim=1, descending=True, stable=True).indices
+                idx = (idx + torch.arange(n_win, device=self.device)[:, None] * W).reshape(-1)
+                order = idx[idx < n_chunks]
+            orders[key] = order.to(torch.int32).contiguous()
+        return orders[key]
 
     # ---- L2 residency classes of the gathered columns (include/lgcn.h, LGCN_COL_*) ----------
     def mark_hot_columns(self, n_hot, col_degree=None):

@@ -19,6 +19,7 @@ from ._lib import SPMM_ADAM, SPMM_ADD, SPMM_MEAN, SPMM_PLAIN, SpmmArgs, check, p
 # CUDA-event profile of the SpMM (bench.py's roofline): set PROFILE to a list to collect
 # (tag, start_event, end_event) on the launching stream.
 COUNTERS = {"launches": 0}
+CHUNK_ORDER_LARGE = bool(os.environ.get("LGCN_CHUNK_ORDER_LARGE"))   # see _spmm_args
 L2_STREAM_BYTES = 96 << 20      # tables larger than this are streamed with L2 evict_first hints
 PROFILE = None
 # L2 budget for the gathered rows of the highest-degree columns (gathered with evict_last; the rows
@@ -126,7 +127,15 @@ def _spmm_args(g, x, mode, d):
         a.seg_len, a.n_seg = g.seg_len, g.n_seg
         a.seg_ws = ptr(g.seg_ws(d))
         a.long_done = ptr(getattr(g, "long_done", None), "i32", allow_none=True)
-    a.chunk_order = ptr(getattr(g, "chunk_order", None), "i32", allow_none=True)
+    # chunk order: on small (L2-resident) graphs a large win (Gowalla step -29 % together with the
+    # in-launch long-row combine); on HBM-streaming graphs the windowed order was measured within
+    # +-5 % per call either way at d/P = 16 / 32 / 64 (profiles/r02_chunk_order_ab.txt: DRAM traffic,
+    # not the idle workers of a warp, bounds those kernels), so it stays opt-in there
+    small = _small_graph(g.n_rows, d)
+    if (small or CHUNK_ORDER_LARGE) and hasattr(g, "chunk_order_for"):
+        rows = _lib.load().lgcn_spmm_chunk_rows(int(g.n_rows), int(d), int(a.flags))
+        if rows > 0:
+            a.chunk_order = ptr(g.chunk_order_for(rows, not small), "i32", allow_none=True)
     return a
 
 

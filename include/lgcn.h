@@ -158,11 +158,14 @@ typedef struct lgcn_spmm_args {
      * not added) is stored to g_skip[(r - skip_begin) * d ...] for the projection's backward. */
     float         *g_skip;
     int64_t        skip_begin, skip_rows;
-    /* Small (L2-resident) graphs only -- ignored on the large-graph path; both optional (NULL).
-     * chunk_order: a permutation of the ceil(n_rows / 4) four-row chunks; worker w takes chunk
-     *   chunk_order[w].  Sorted by descending entry count it pairs chunks of equal length in a warp
-     *   and schedules the longest work first.  Results do not depend on it.
-     * long_done: n_long zero-initialised counters.  When given, the worker that stores the LAST
+    /* Work plan, both optional (NULL).
+     * chunk_order: a permutation of the ceil(n_rows / R) chunks of R consecutive rows, R =
+     *   lgcn_spmm_chunk_rows(n_rows, d, flags); worker w takes chunk chunk_order[w].  Tables narrower
+     *   than 128 floats put several workers in one warp, which then walks to the longest of their
+     *   chunks: an order that puts chunks of similar entry count next to each other (sorted inside
+     *   windows, so that the streams stay local) removes that idling.  Results do not depend on it.
+     *   Ignored when lgcn_spmm_chunk_rows() returns 0.
+     * long_done (small, L2-resident graphs only): n_long zero-initialised counters.  When given, the worker that stores the LAST
      *   segment partial of a long row combines the row's partials (in segment order, as the combine
      *   launch would) and runs its epilogue, then re-arms the counter: no separate combine launch.
      *   One concurrent lgcn_spmm call per counter array. */
@@ -192,11 +195,14 @@ typedef struct lgcn_spmm_args {
 LGCN_API int lgcn_spmm(const lgcn_spmm_args *args_host, lgcn_stream_t stream);
 /* sizeof(lgcn_spmm_args) as compiled, so that a binding can verify its struct layout */
 LGCN_API size_t lgcn_sizeof_spmm_args(void);
+/* Host-only query: rows per chunk that lgcn_spmm_args.chunk_order permutes for this graph size,
+ * width and flags; 0 when the kernel that will run ignores chunk_order; negative LGCN_E_* code. */
+LGCN_API int lgcn_spmm_chunk_rows(int64_t n_rows, int32_t d, int32_t flags);
 /* Host-only query (launches nothing): how many kernels one lgcn_spmm call launches for a graph of
  * n_rows rows with n_long long rows at width d under `flags` (1 = main kernel; with long rows
- * 3 = segments + main + combine, or 2 on small graphs whose segment workers ride in the main
- * launch).  *small_path (optional) = 1 when the small-graph 4-row-chunk path is taken.  Returns
- * the count (> 0) or a negative LGCN_E_* code. */
+ * 3 = segments + main + combine, on small graphs 2 -- the segment workers ride in the main launch --
+ * or 1 with LGCN_SPMM_F_LONG_DONE).  *small_path (optional) = 1 when the small-graph 4-row-chunk
+ * path is taken.  Returns the count (> 0) or a negative LGCN_E_* code. */
 LGCN_API int lgcn_spmm_launches(int64_t n_rows, int32_t d, int32_t n_long, int32_t flags,
                        int32_t *small_path);
 /* Host-only query: the name of the MAIN kernel lgcn_spmm selects for this shape / mode (what a

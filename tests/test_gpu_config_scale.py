@@ -281,10 +281,11 @@ def test_small_graph_plan_is_result_neutral_at_gowalla_shape(gowalla, dev, monke
     monkeypatch.setenv("LGCN_NO_SMALL_PLAN", "1")
     plain = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev)
     monkeypatch.delenv("LGCN_NO_SMALL_PLAN")
-    assert planned.chunk_order is not None and planned.long_done is not None and planned.n_long > 0
-    assert plain.chunk_order is None and plain.long_done is None
-    order = planned.chunk_order.cpu().numpy()
-    assert np.array_equal(np.sort(order), np.arange((planned.n_rows + 3) // 4))
+    assert planned.long_done is not None and planned.n_long > 0 and plain.long_done is None
+    for R, windowed in ((4, False), (4, True), (8, True)):
+        order = planned.chunk_order_for(R, windowed).cpu().numpy()
+        assert np.array_equal(np.sort(order), np.arange((planned.n_rows + R - 1) // R))
+    assert plain.chunk_order_for(4, False) is None
     N = planned.n_rows
     gen = torch.Generator(device=dev).manual_seed(7)
     for d in (64, 16, 128):
@@ -308,3 +309,62 @@ def test_small_graph_plan_is_result_neutral_at_gowalla_shape(gowalla, dev, monke
         for t0, t1 in zip(*outs):
             assert torch.equal(t0, t1)
         assert int(planned.long_done.abs().sum()) == 0
+
+
+def test_chunk_order_is_result_neutral_on_the_large_graph_kernels(dev, monkeypatch):
+    """Amazon shape at 1/16 scale, narrow (feature-sharded) tables: the ring / live-list kernels put
+    8 / 4 / 2 workers in a warp and follow ``chunk_order`` (windowed sort by entry count).  Every
+    mode, dense and sparse hops, must be bit-identical with and without the order."""
+    from gcn_recommendation_b200 import _lib, ops, synth
+    from gcn_recommendation_b200.graph import NormAdjCSR
+    U, I, B, total, _, K = synth.SHAPES["amazon_16th"]
+    inter = synth.generate("amazon_16th", seed=0)
+    tu, ti, vu, vi = inter.split_validation()
+    ordered = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev)
+    monkeypatch.setenv("LGCN_NO_CHUNK_ORDER", "1")
+    natural = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev)
+    monkeypatch.delenv("LGCN_NO_CHUNK_ORDER")
+    monkeypatch.setattr(ops, "CHUNK_ORDER_LARGE", True)       # opt-in on HBM-streaming graphs
+    N = ordered.n_rows
+    lib = _lib.load()
+    gen = torch.Generator(device=dev).manual_seed(3)
+    for d, rows in ((16, 4), (32, 8), (64, 8), (128, 0)):
+        flags = ops.SPMM_FLAGS_EXTRA | (_lib.SPMM_F_STREAM_HINTS if N * d * 4 > ops.L2_STREAM_BYTES else 0)
+        assert lib.lgcn_spmm_chunk_rows(N, d, flags) == rows
+        if rows == 0:
+            continue
+        order = ordered.chunk_order_for(rows, True).cpu().numpy()
+        assert np.array_equal(np.sort(order), np.arange((N + rows - 1) // rows))
+        assert natural.chunk_order_for(rows, True) is None
+        x = torch.randn((N, d), device=dev, generator=gen)
+        a1 = torch.randn((N, d), device=dev, generator=gen)
+        y0, y1 = ops.spmm(natural, x), ops.spmm(ordered, x)
+        assert torch.equal(y0, y1)
+        assert torch.equal(ops.spmm(natural, x, addend=a1), ops.spmm(ordered, x, addend=a1))
+        assert torch.equal(ops.spmm(natural, y0, mean_layers=[x, y0]), ops.spmm(ordered, y0, mean_layers=[x, y0]))
+        # sparse hop (live-list kernel): x and the addend non-zero on a few thousand flagged rows
+        hot = torch.randint(0, N, (6144,), device=dev, generator=gen)
+        xs = torch.zeros((N, d), device=dev)
+        xs[hot] = torch.randn((hot.numel(), d), device=dev, generator=gen)
+        flag = torch.zeros(N + 32, dtype=torch.uint8, device=dev)
+        flag[hot] = 1
+        zr = torch.zeros(256, device=dev)
+        outs = []
+        for gr in (natural, ordered):
+            yf = torch.zeros(N + 32, dtype=torch.uint8, device=dev)
+            y = torch.zeros((N, d), device=dev)
+            ops.spmm(gr, xs, out=y, addend=xs, x_rowflag=flag, addend_rowflag=flag, zero_row=zr, y_rowflag=yf)
+            y2 = ops.spmm(gr, y, addend=xs, x_rowflag=yf, addend_rowflag=flag, zero_row=zr)
+            outs.append((y, yf, y2))
+        for t0, t1 in zip(*outs):
+            assert torch.equal(t0, t1)
+        sc = torch.zeros(2, device=dev)
+        step = torch.zeros(1, dtype=torch.int64, device=dev)
+        ops.adam_tick(step, sc, 1e-3, (0.9, 0.999))
+        res = []
+        for gr in (natural, ordered):
+            p, m, v = a1.clone(), torch.zeros_like(a1), torch.zeros_like(a1)
+            ops.spmm_adam(gr, x, p, m, v, sc, addend=a1)
+            res.append((p, m, v))
+        for t0, t1 in zip(*res):
+            assert torch.equal(t0, t1)

@@ -46,6 +46,11 @@ def test_spmm_plan_query_matches_documented_selection():
     finally:
         ops.SPMM_FLAGS_EXTRA = old
     assert _lib.load().lgcn_spmm_launches(10, 48, 0, 0, None) == -1
+    # rows per chunk that lgcn_spmm_args.chunk_order permutes (0 = the kernel ignores the order)
+    rows = _lib.load().lgcn_spmm_chunk_rows
+    assert rows(70_840, 64, 0) == 4 and rows(70_840, 16, 0) == 4
+    assert [rows(14_700_001, d, 0) for d in (16, 32, 64, 128, 256)] == [4, 8, 8, 0, 0]
+    assert rows(14_700_001, 16, _lib.SPMM_F_NO_RING) == 0 and rows(10, 48, 0) == -1
 
 
 def test_argument_errors_are_reported_not_thrown():
