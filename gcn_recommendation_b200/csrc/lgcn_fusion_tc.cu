@@ -7,7 +7,7 @@
 // lo.wlo term and the truncation of lo are ~2^-21 relative).  The concatenation is never
 // materialised and the 13.5 GB content matrix is streamed exactly once.
 //
-// CTA (persistent over 128-item tiles): 8 loader warps read fp32 rows (E_id for k < d, content
+// CTA (persistent over 128-item tiles): 16 loader warps read fp32 rows (E_id for k < d, content
 // for k >= d; W rows likewise), split them and write hi / lo straight into the UMMA K-major
 // SWIZZLE_128B layout in shared memory (generic-proxy stores + fence.proxy.async); one
 // thread issues 12 tcgen05.mma.kind::tf32 (128 x d x 8) per 32-wide K chunk into one of two TMEM
@@ -213,10 +213,10 @@ fusion_fwd_tc_kernel(const float *__restrict__ Eid, const float *__restrict__ Cm
             split_store(hi_dst + off, lo_dst + off, x);
         };
         // Three register buffers used IN PLACE: a buffer is refilled with the chunk three ahead right
-        // after it has been stored (no register copies that wait for the newest load).  Measured
-        // neutral (11.5 -> 11.4 ms): the loaders are not latency bound -- ncu r02 shows the LSU data
-        // pipe at 96 % (l1tex__data_pipe_lsu_wavefronts), three quarters of it the wavefronts of these
-        // global loads (8 rows x 64 bytes per LDG.128), see profiles/r02_fusion_notes.txt.
+        // after it has been stored (no register copies that wait for the newest load).  (History,
+        // profiles/r02_fusion_notes.txt: with round 1's load mapping -- 8 rows x 64 bytes per LDG.128 --
+        // the LSU data pipe was 96 % busy and this rotation measured neutral; after the quarter-warp
+        // remapping and the swizzled stores the loaders are latency bound, hence 16 of them.)
         float4 xa[NA], xb[NBT], ya[NA], yb[NBT], za[NA], zb[NBT];
         auto advance = [&](int64_t &t, int &c_) {
             if (++c_ == n_chunks) { c_ = 0; t += gridDim.x; }
