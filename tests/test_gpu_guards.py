@@ -93,6 +93,13 @@ def _guarded_graph(G, csr):
         csr.long_rowptr = G.inp(csr.long_rowptr.cpu().numpy())
         csr.long_colval = G.inp(csr.long_colval.cpu().numpy())
         csr.long_seg_ptr = G.inp(csr.long_seg_ptr.cpu().numpy())
+        if csr.long_done is not None:                   # ABI v7 work plan: counters (written), orders (read)
+            csr.long_done = G.out((csr.n_long,), torch.int32, fill=0)
+    for rows in (4, 8):
+        for windowed in (False, True):
+            order = csr.chunk_order_for(rows, windowed)
+            if order is not None:
+                csr._chunk_orders[(rows, windowed)] = G.inp(order.cpu().numpy())
     return csr
 
 
@@ -111,9 +118,10 @@ def test_spmm_stays_inside_its_buffers(dev, d, path):
     X = rng.standard_normal((N, d), dtype=np.float32)
     A1 = rng.standard_normal((N, d), dtype=np.float32)
     ref = orc.spmm(a["rowptr"], a["col"], a["val"], X)
-    old = ops.SPMM_FLAGS_EXTRA
+    old, old_large = ops.SPMM_FLAGS_EXTRA, ops.CHUNK_ORDER_LARGE
     ops.SPMM_FLAGS_EXTRA = {"small": 0, "ring": _lib.SPMM_F_BIG_PATH | _lib.SPMM_F_FORCE_RING,
                             "chunk": _lib.SPMM_F_BIG_PATH | _lib.SPMM_F_NO_RING}[path]
+    ops.CHUNK_ORDER_LARGE = True                     # the ring / live kernels follow a (guarded) order too
     try:
         G = Guarded(dev)
         csr = _guarded_graph(G, NormAdjCSR.from_interactions(tu, ti, U, I, B, dev, long_row_threshold=48, seg_len=32))
@@ -157,8 +165,10 @@ def test_spmm_stays_inside_its_buffers(dev, d, path):
         G.check()
         assert rel_err(gout.cpu().numpy(), ref + A1)[0] < 1e-5
         assert torch.isfinite(p).all() and torch.isfinite(m).all() and torch.isfinite(v).all()
+        if csr.long_done is not None:
+            assert int(csr.long_done.abs().sum()) == 0, "long-row counters must be re-armed"
     finally:
-        ops.SPMM_FLAGS_EXTRA = old
+        ops.SPMM_FLAGS_EXTRA, ops.CHUNK_ORDER_LARGE = old, old_large
 
 
 @pytest.mark.parametrize("d", [16, 64, 128])
