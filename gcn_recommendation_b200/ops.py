@@ -19,7 +19,7 @@ from ._lib import SPMM_ADAM, SPMM_ADD, SPMM_MEAN, SPMM_PLAIN, SpmmArgs, check, p
 # CUDA-event profile of the SpMM (bench.py's roofline): set PROFILE to a list to collect
 # (tag, start_event, end_event) on the launching stream.
 COUNTERS = {"launches": 0}
-CHUNK_ORDER_LARGE = bool(os.environ.get("LGCN_CHUNK_ORDER_LARGE"))   # see _spmm_args
+CHUNK_ORDER_LARGE = os.environ.get("LGCN_CHUNK_ORDER_LARGE", "auto")   # auto | all | off, see _set_chunk_order
 L2_STREAM_BYTES = 96 << 20      # tables larger than this are streamed with L2 evict_first hints
 PROFILE = None
 # L2 budget for the gathered rows of the highest-degree columns (gathered with evict_last; the rows
@@ -94,6 +94,7 @@ def spmm_launches(g, d):
 
 
 def _launch_spmm(a, g, dev, tag):
+    _set_chunk_order(a, g)
     n_kernels = spmm_launches(g, a.d)
     COUNTERS["launches"] += n_kernels
     if PROFILE is None:
@@ -127,16 +128,30 @@ def _spmm_args(g, x, mode, d):
         a.seg_len, a.n_seg = g.seg_len, g.n_seg
         a.seg_ws = ptr(g.seg_ws(d))
         a.long_done = ptr(getattr(g, "long_done", None), "i32", allow_none=True)
-    # chunk order: on small (L2-resident) graphs a large win (Gowalla step -29 % together with the
-    # in-launch long-row combine); on HBM-streaming graphs the windowed order was measured within
-    # +-5 % per call either way at d/P = 16 / 32 / 64 (profiles/r02_chunk_order_ab.txt: DRAM traffic,
-    # not the idle workers of a warp, bounds those kernels), so it stays opt-in there
-    small = _small_graph(g.n_rows, d)
-    if (small or CHUNK_ORDER_LARGE) and hasattr(g, "chunk_order_for"):
-        rows = _lib.load().lgcn_spmm_chunk_rows(int(g.n_rows), int(d), int(a.flags))
-        if rows > 0:
-            a.chunk_order = ptr(g.chunk_order_for(rows, not small), "i32", allow_none=True)
     return a
+
+
+def _set_chunk_order(a, g):
+    """``lgcn_spmm_args.chunk_order`` (include/lgcn.h).  Small (L2-resident) graphs: always (Gowalla
+    step -29 % together with the in-launch long-row combine).  HBM-streaming graphs with several
+    workers per warp (d/P <= 64): the windowed order balances the workers but scatters each warp's
+    chunks, which costs the coalescing of the entry stream -- measured per call at the Amazon shape
+    (profiles/r02_chunk_order_ab.txt): launches with many streamed bytes per chunk (MEAN -3..-12 %,
+    ADAM 0..-7 %) and the flagged walk with dense output (hop 2: -1..-15 %) gain at every width,
+    pure gather launches (PLAIN / dense ADD at d/P = 16: +5..9 %) and the sparse-output hop (+10..18 %
+    at d/P >= 32) lose.  ``auto`` follows that table; LGCN_CHUNK_ORDER_LARGE = all | off overrides."""
+    if not hasattr(g, "chunk_order_for"):
+        return
+    small = _small_graph(g.n_rows, a.d)
+    if not small:
+        if CHUNK_ORDER_LARGE == "off":
+            return
+        if CHUNK_ORDER_LARGE != "all" and not (
+                a.mode in (SPMM_MEAN, SPMM_ADAM) or (a.x_rowflag and not a.y_rowflag)):
+            return
+    rows = _lib.load().lgcn_spmm_chunk_rows(int(g.n_rows), int(a.d), int(a.flags))
+    if rows > 0:
+        a.chunk_order = ptr(g.chunk_order_for(rows, not small), "i32", allow_none=True)
 
 
 def spmm_kernel_name(g, d, mode, sparse_x=False):

@@ -324,7 +324,7 @@ def test_chunk_order_is_result_neutral_on_the_large_graph_kernels(dev, monkeypat
     monkeypatch.setenv("LGCN_NO_CHUNK_ORDER", "1")
     natural = NormAdjCSR.from_interactions(tu, ti, U, I, B, dev)
     monkeypatch.delenv("LGCN_NO_CHUNK_ORDER")
-    monkeypatch.setattr(ops, "CHUNK_ORDER_LARGE", True)       # opt-in on HBM-streaming graphs
+    monkeypatch.setattr(ops, "CHUNK_ORDER_LARGE", "all")      # every mode, not only the ones "auto" picks
     N = ordered.n_rows
     lib = _lib.load()
     gen = torch.Generator(device=dev).manual_seed(3)

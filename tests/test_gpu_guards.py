@@ -121,7 +121,7 @@ def test_spmm_stays_inside_its_buffers(dev, d, path):
     old, old_large = ops.SPMM_FLAGS_EXTRA, ops.CHUNK_ORDER_LARGE
     ops.SPMM_FLAGS_EXTRA = {"small": 0, "ring": _lib.SPMM_F_BIG_PATH | _lib.SPMM_F_FORCE_RING,
                             "chunk": _lib.SPMM_F_BIG_PATH | _lib.SPMM_F_NO_RING}[path]
-    ops.CHUNK_ORDER_LARGE = True                     # the ring / live kernels follow a (guarded) order too
+    ops.CHUNK_ORDER_LARGE = "all"                    # the ring / live kernels follow a (guarded) order too
     try:
         G = Guarded(dev)
         csr = _guarded_graph(G, NormAdjCSR.from_interactions(tu, ti, U, I, B, dev, long_row_threshold=48, seg_len=32))
