@@ -331,3 +331,41 @@ def test_mask_csr_builders_agree():
     assert np.array_equal(rp1.numpy(), rp3) and np.array_equal(c1.numpy(), c3)
     assert np.array_equal(rp2.numpy(), rp3) and np.array_equal(c2.numpy(), c3)
     assert c1.dtype == torch.int32 and rp1.dtype == torch.int64
+
+
+def test_chunk_order_policy_is_host_logic(monkeypatch):
+    """``ops._set_chunk_order`` (no GPU): small graphs always get the global order; HBM-streaming
+    graphs get the windowed order only for MEAN / ADAM launches and the flagged walk with dense
+    output, never at d = 128 (one worker per warp) -- profiles/r02_chunk_order_ab.txt."""
+    from gcn_recommendation_b200 import _lib, ops
+
+    class FakeGraph:
+        def __init__(self, n_rows):
+            self.n_rows = n_rows
+            self.asked = []
+
+        def chunk_order_for(self, rows, windowed):
+            self.asked.append((rows, windowed))
+            return ("order", rows, windowed)
+
+    monkeypatch.setattr(ops, "ptr", lambda t, *a, **k: 1234 if t is not None else None)
+
+    def run(n_rows, d, mode, x_rowflag=None, y_rowflag=None, policy="auto"):
+        monkeypatch.setattr(ops, "CHUNK_ORDER_LARGE", policy)
+        g = FakeGraph(n_rows)
+        a = _lib.SpmmArgs()
+        a.n_rows, a.d, a.mode, a.flags = n_rows, d, mode, 0
+        a.x_rowflag, a.y_rowflag = x_rowflag, y_rowflag
+        ops._set_chunk_order(a, g)
+        return g.asked
+
+    assert run(70_840, 64, ops.SPMM_PLAIN) == [(4, False)]                 # small graph: every mode
+    assert run(70_840, 64, ops.SPMM_ADAM) == [(4, False)]
+    big = 14_700_001
+    assert run(big, 16, ops.SPMM_PLAIN) == [] and run(big, 16, ops.SPMM_ADD) == []
+    assert run(big, 16, ops.SPMM_MEAN) == [(4, True)] and run(big, 32, ops.SPMM_ADAM) == [(8, True)]
+    assert run(big, 64, ops.SPMM_ADD, x_rowflag=1) == [(8, True)]          # hop 2: flagged in, dense out
+    assert run(big, 64, ops.SPMM_ADD, x_rowflag=1, y_rowflag=1) == []      # hop 1: sparse out
+    assert run(big, 128, ops.SPMM_MEAN) == []                              # one worker per warp
+    assert run(big, 16, ops.SPMM_PLAIN, policy="all") == [(4, True)]
+    assert run(big, 16, ops.SPMM_MEAN, policy="off") == []
