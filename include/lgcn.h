@@ -165,10 +165,11 @@ typedef struct lgcn_spmm_args {
      *   chunks: an order that puts chunks of similar entry count next to each other (sorted inside
      *   windows, so that the streams stay local) removes that idling.  Results do not depend on it.
      *   Ignored when lgcn_spmm_chunk_rows() returns 0.
-     * long_done (small, L2-resident graphs only): n_long zero-initialised counters.  When given, the worker that stores the LAST
-     *   segment partial of a long row combines the row's partials (in segment order, as the combine
-     *   launch would) and runs its epilogue, then re-arms the counter: no separate combine launch.
-     *   One concurrent lgcn_spmm call per counter array. */
+     * long_done (used on small, L2-resident graphs only): n_long zero-initialised counters.  When
+     *   given, the worker that stores the LAST segment partial of a long row combines the row's
+     *   partials (in segment order, as the combine launch would) and runs its epilogue, then
+     *   re-arms the counter: no separate combine launch.  One concurrent lgcn_spmm call per
+     *   counter array. */
     const int32_t *chunk_order;
     int32_t       *long_done;
 } lgcn_spmm_args;
@@ -182,9 +183,9 @@ typedef struct lgcn_spmm_args {
 #define LGCN_SPMM_F_COLD_FIRST 8    /* gathers of unclassified columns use evict_first too   */
 #define LGCN_SPMM_F_FORCE_RING 16   /* (no-op since ABI v5: the ring kernel serves ADAM too)  */
 #define LGCN_SPMM_F_NO_PREFETCH 32  /* no L2 prefetch of the epilogue operands (A/B only)    */
-#define LGCN_SPMM_F_LONG_DONE 256   /* lgcn_spmm_launches() only: the call will pass long_done */
 #define LGCN_SPMM_F_ALT_X 64        /* gathers of rows in the alt range read x_alt           */
 #define LGCN_SPMM_F_ALT_LAYER0 128  /* MEAN: layers[0] rows in the alt range read x_alt      */
+#define LGCN_SPMM_F_LONG_DONE 256   /* lgcn_spmm_launches() only: the call will pass long_done */
 
 #define LGCN_SPMM_PLAIN 0 /* y = A x                                                    */
 #define LGCN_SPMM_ADD   1 /* y = addend + A x              (Horner backward hop)        */
